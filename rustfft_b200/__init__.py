@@ -1,0 +1,307 @@
+"""rustfft_b200 -- B200-native batched complex FFT behind RustFFT's FftPlanner / Fft interface.
+
+Host-side mirror (Python, because the image has no Rust toolchain) of the reference's public
+API for the hot path; the names, argument meaning and error behaviour follow the reference
+(paths relative to the RustFFT 6.4.1 tree):
+
+    FftPlanner.plan_fft / plan_fft_forward / plan_fft_inverse      src/plan.rs:67-126
+    Fft.process / process_with_scratch                             src/lib.rs:195-211
+    Fft.process_outofplace_with_scratch                            src/lib.rs:231-236
+    Fft.process_immutable_with_scratch                             src/lib.rs:250-255
+    Fft.get_{inplace,outofplace,immutable}_scratch_len             src/lib.rs:262-277
+    Fft.len / Fft.fft_direction                                    src/lib.rs:140-181
+    FftDirection                                                   src/lib.rs:147-171
+
+Everything numeric happens in rustfft_b200/libb200fft.so (hand-written sm_100a CUDA behind the
+C ABI of include/b200fft.h).  There is no CPU fallback: without the library or without a B200
+the planner raises.  PyTorch is only used for device memory / streams by callers (tests, bench).
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "default_library", "shard_range"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB_PATH = os.path.join(_HERE, "libb200fft.so")
+
+F32, F64 = 0, 1
+
+
+class FftError(RuntimeError):
+    """Raised where the reference panics (src/common.rs:13-104) or where CUDA fails."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+class FftDirection(enum.IntEnum):
+    Forward = 0
+    Inverse = 1
+
+    def opposite_direction(self) -> "FftDirection":  # src/lib.rs:156-161
+        return FftDirection.Inverse if self == FftDirection.Forward else FftDirection.Forward
+
+
+class Library:
+    """A loaded C-ABI library (include/b200fft.h)."""
+
+    SYMBOLS = [
+        "b200fft_device_count", "b200fft_plan_create", "b200fft_plan_destroy", "b200fft_plan_len",
+        "b200fft_plan_direction", "b200fft_plan_precision", "b200fft_plan_scratch_len", "b200fft_plan_describe",
+        "b200fft_plan_launches", "b200fft_exec_host_inplace", "b200fft_exec_host_outofplace", "b200fft_exec_device",
+        "b200fft_workspace_bytes", "b200fft_exec_device_ws", "b200fft_last_error", "b200fft_version",
+    ]
+
+    def __init__(self, path: str = DEFAULT_LIB_PATH):
+        if not os.path.exists(path):
+            raise FftError(-2, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        self.path = path
+        self.c = ctypes.CDLL(path)
+        c, u64, i32, vp = self.c, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p
+        c.b200fft_device_count.argtypes = [ctypes.POINTER(i32)]
+        c.b200fft_plan_create.argtypes = [ctypes.POINTER(vp), u64, i32, i32, i32]
+        c.b200fft_plan_destroy.argtypes = [vp]
+        c.b200fft_plan_len.argtypes = [vp]
+        c.b200fft_plan_len.restype = u64
+        c.b200fft_plan_direction.argtypes = [vp]
+        c.b200fft_plan_precision.argtypes = [vp]
+        c.b200fft_plan_scratch_len.argtypes = [vp, i32]
+        c.b200fft_plan_scratch_len.restype = u64
+        c.b200fft_plan_describe.argtypes = [vp, ctypes.c_char_p, u64]
+        c.b200fft_plan_launches.argtypes = [vp, u64]
+        c.b200fft_plan_launches.restype = u64
+        c.b200fft_exec_host_inplace.argtypes = [vp, vp, u64]
+        c.b200fft_exec_host_outofplace.argtypes = [vp, vp, vp, u64]
+        c.b200fft_exec_device.argtypes = [vp, vp, vp, u64, vp]
+        c.b200fft_workspace_bytes.argtypes = [vp, u64]
+        c.b200fft_workspace_bytes.restype = u64
+        c.b200fft_exec_device_ws.argtypes = [vp, vp, vp, u64, vp, vp, u64]
+        c.b200fft_last_error.restype = ctypes.c_char_p
+        c.b200fft_version.restype = ctypes.c_char_p
+
+    def device_count(self) -> int:
+        n = ctypes.c_int(0)
+        self.check(self.c.b200fft_device_count(ctypes.byref(n)))
+        return n.value
+
+    def version(self) -> str:
+        return self.c.b200fft_version().decode()
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise FftError(rc, self.c.b200fft_last_error().decode())
+
+
+_default: Optional[Library] = None
+_default_lock = threading.Lock()
+
+
+def default_library() -> Library:
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = Library(DEFAULT_LIB_PATH)
+        return _default
+
+
+_DTYPES = {np.dtype(np.complex64): F32, np.dtype(np.complex128): F64}
+
+
+class Fft:
+    """One planned transform: the Arc<dyn Fft<T>> of the reference (src/lib.rs:184-278).
+
+    Immutable after construction and safe to call from many threads (examples/concurrency.rs)."""
+
+    def __init__(self, lib: Library, length: int, direction: FftDirection, precision: int, device: int):
+        self._lib = lib
+        self._h = ctypes.c_void_p()
+        lib.check(lib.c.b200fft_plan_create(ctypes.byref(self._h), length, int(direction), precision, device))
+        self._len = length
+        self._direction = FftDirection(direction)
+        self._precision = precision
+        self.device = device
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.c.b200fft_plan_destroy(h)
+            except Exception:
+                pass
+
+    # ---- Length / Direction ------------------------------------------------------------
+    def len(self) -> int:
+        return self._len
+
+    def __len__(self) -> int:
+        return self._len
+
+    def fft_direction(self) -> FftDirection:
+        return self._direction
+
+    @property
+    def dtype(self):
+        return np.complex64 if self._precision == F32 else np.complex128
+
+    def describe(self) -> str:
+        buf = ctypes.create_string_buffer(512)
+        rc = self._lib.c.b200fft_plan_describe(self._h, buf, len(buf))
+        if rc < 0:
+            self._lib.check(rc)
+        return buf.value.decode()
+
+    def launches(self, batch: int) -> int:
+        return int(self._lib.c.b200fft_plan_launches(self._h, batch))
+
+    # ---- scratch getters: this backend needs no caller scratch (allowed, src/lib.rs:259-261)
+    def get_inplace_scratch_len(self) -> int:
+        return int(self._lib.c.b200fft_plan_scratch_len(self._h, 0))
+
+    def get_outofplace_scratch_len(self) -> int:
+        return int(self._lib.c.b200fft_plan_scratch_len(self._h, 1))
+
+    def get_immutable_scratch_len(self) -> int:
+        return int(self._lib.c.b200fft_plan_scratch_len(self._h, 2))
+
+    # ---- host-slice trait methods ------------------------------------------------------
+    def _host(self, a, name: str, writable: bool) -> np.ndarray:
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(self.dtype) or a.ndim != 1 or not a.flags.c_contiguous:
+            raise TypeError(f"{name} must be a contiguous 1-D numpy array of {np.dtype(self.dtype).name}")
+        if writable and not a.flags.writeable:
+            raise TypeError(f"{name} must be writable")
+        return a
+
+    def _check_scratch(self, scratch, need: int) -> None:
+        # "Not enough scratch space was provided..." (src/common.rs:32-37); need is 0 here, so any
+        # scratch (even dirty, src/test_utils.rs:131-141) is accepted and ignored.
+        if scratch is not None and len(scratch) < need:
+            raise FftError(-9, f"Not enough scratch space was provided. Expected scratch len >= {need}, "
+                               f"got scratch len = {len(scratch)}")
+
+    def process(self, buffer: np.ndarray) -> None:
+        """In place over every contiguous chunk of len() elements (src/lib.rs:195-198)."""
+        self.process_with_scratch(buffer, None)
+
+    def process_with_scratch(self, buffer: np.ndarray, scratch=None) -> None:
+        buffer = self._host(buffer, "buffer", True)
+        self._check_scratch(scratch, self.get_inplace_scratch_len())
+        self._lib.check(self._lib.c.b200fft_exec_host_inplace(self._h, buffer.ctypes.data, buffer.size))
+
+    def process_outofplace_with_scratch(self, input: np.ndarray, output: np.ndarray, scratch=None) -> None:
+        """input may be used as scratch by the reference (src/lib.rs:213-236); here it is left intact."""
+        input = self._host(input, "input", True)
+        output = self._host(output, "output", True)
+        self._check_scratch(scratch, self.get_outofplace_scratch_len())
+        if input.size != output.size:
+            raise FftError(-6, "Provided FFT input buffer and output buffer must have the same length. "
+                               f"Got input.len() = {input.size}, output.len() = {output.size}")
+        self._lib.check(self._lib.c.b200fft_exec_host_outofplace(self._h, input.ctypes.data, output.ctypes.data, input.size))
+
+    def process_immutable_with_scratch(self, input: np.ndarray, output: np.ndarray, scratch=None) -> None:
+        input = self._host(input, "input", False)
+        output = self._host(output, "output", True)
+        self._check_scratch(scratch, self.get_immutable_scratch_len())
+        if input.size != output.size:
+            raise FftError(-6, "Provided FFT input buffer and output buffer must have the same length. "
+                               f"Got input.len() = {input.size}, output.len() = {output.size}")
+        self._lib.check(self._lib.c.b200fft_exec_host_outofplace(self._h, input.ctypes.data, output.ctypes.data, input.size))
+
+    # ---- device-resident path (no reference equivalent; the measured one) --------------
+    def workspace_bytes(self, batch: int) -> int:
+        return int(self._lib.c.b200fft_workspace_bytes(self._h, batch))
+
+    def process_device_ptr(self, d_in: int, d_out: int, batch: int, stream: int = 0,
+                           workspace: int = 0, workspace_bytes: int = 0) -> None:
+        """Raw pointers on the plan's device, batch*len() elements each, async on `stream`."""
+        if workspace:
+            rc = self._lib.c.b200fft_exec_device_ws(self._h, d_in, d_out, batch, stream, workspace, workspace_bytes)
+        else:
+            rc = self._lib.c.b200fft_exec_device(self._h, d_in, d_out, batch, stream)
+        self._lib.check(rc)
+
+    def process_device(self, x, out=None, workspace=None):
+        """x: torch complex tensor on the plan's device holding batch*len() elements (any shape,
+        contiguous).  In place when `out` is None.  Asynchronous on torch's current stream."""
+        import torch
+
+        want = torch.complex64 if self._precision == F32 else torch.complex128
+        if x.dtype != want or not x.is_cuda or not x.is_contiguous():
+            raise TypeError(f"process_device wants a contiguous CUDA tensor of {want}")
+        if x.device.index != self.device:
+            raise FftError(-1, f"tensor is on cuda:{x.device.index}, plan is on cuda:{self.device}")
+        dst = x if out is None else out
+        if dst.dtype != want or dst.numel() != x.numel() or not dst.is_contiguous() or dst.device != x.device:
+            raise FftError(-6, "Provided FFT input buffer and output buffer must have the same length. "
+                               f"Got input.len() = {x.numel()}, output.len() = {dst.numel()}")
+        n = x.numel()
+        if self._len == 0 or n == 0:
+            return dst
+        if n < self._len:
+            raise FftError(-4, f"Provided FFT buffer was too small. Expected len = {self._len}, got len = {n}")
+        if n % self._len:
+            raise FftError(-5, "Input FFT buffer must be a multiple of FFT length. "
+                               f"Expected multiple of {self._len}, got len = {n}")
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        ws_ptr, ws_bytes = 0, 0
+        if workspace is not None:
+            ws_ptr, ws_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+        self.process_device_ptr(x.data_ptr(), dst.data_ptr(), n // self._len, stream, ws_ptr, ws_bytes)
+        return dst
+
+
+class FftPlanner:
+    """FftPlanner<T> of the reference (src/plan.rs:67-126) for this backend.
+
+    Like FftPlannerAvx::new() (src/avx/avx_planner.rs:121-164) construction fails when the hardware
+    is absent -- the reference would then fall through to its next backend; here it raises, because
+    this package has no other backend.  Plans are cached per (len, direction) exactly like
+    FftCache (src/fft_cache.rs:5-38): planning the same transform twice returns the same object."""
+
+    def __init__(self, dtype=np.complex64, device: int = 0, lib: Optional[Library] = None):
+        dt = np.dtype(dtype)
+        if dt == np.dtype(np.float32):
+            dt = np.dtype(np.complex64)
+        if dt == np.dtype(np.float64):
+            dt = np.dtype(np.complex128)
+        if dt not in _DTYPES:
+            raise TypeError("FftPlanner accelerates f32 and f64 only (src/avx/avx_planner.rs:149-163)")
+        self._precision = _DTYPES[dt]
+        self._lib = lib if lib is not None else default_library()
+        if self._lib.device_count() <= 0:
+            raise FftError(-2, "no sm_100 CUDA device is visible (there is no CPU fallback)")
+        self.device = device
+        self._cache: Dict[Tuple[int, int], Fft] = {}
+        self._lock = threading.Lock()
+
+    def plan_fft(self, len: int, direction: FftDirection) -> Fft:
+        key = (int(len), int(direction))
+        with self._lock:
+            fft = self._cache.get(key)
+            if fft is None:
+                fft = Fft(self._lib, int(len), FftDirection(direction), self._precision, self.device)
+                self._cache[key] = fft
+            return fft
+
+    def plan_fft_forward(self, len: int) -> Fft:
+        return self.plan_fft(len, FftDirection.Forward)
+
+    def plan_fft_inverse(self, len: int) -> Fft:
+        return self.plan_fft(len, FftDirection.Inverse)
+
+
+def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch shard [lo, hi) of `rank` (remainder to the low ranks): transforms in a
+    batch are independent (src/array_utils.rs:164-170 is a plain loop), so a batch shards across
+    GPUs with no data-path collective."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,105 @@
+// libb200fft.so -- CUDA translation unit: the `rt::` layer on the CUDA runtime + every sm_100a kernel
+// instantiation (through impl.inl).  Build: see rustfft_b200/csrc/Makefile
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+
+#include "common.h"
+
+namespace b2 {
+namespace rt {
+
+typedef cudaStream_t stream_t;
+
+static thread_local std::string g_err;
+static bool check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return false;
+}
+static std::string last_error() { return g_err; }
+
+// devices this library can run on: compute capability 10.x (the cubin is sm_100a only)
+static int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++usable;
+        else break;  // keep device indices dense
+    }
+    return usable;
+}
+static bool set_device(int d) { return check(cudaSetDevice(d), "cudaSetDevice"); }
+static void* dmalloc(size_t bytes) {
+    void* p = nullptr;
+    if (!check(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
+    return p;
+}
+static void dfree(void* p) { cudaFree(p); }
+static bool h2d_sync(void* d, const void* h, size_t n) { return check(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice), "cudaMemcpy H2D"); }
+static bool h2d_async(void* d, const void* h, size_t n, stream_t s) {
+    return check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
+}
+static bool d2h_async(void* h, const void* d, size_t n, stream_t s) {
+    return check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
+}
+static bool d2d_async(void* dst, const void* src, size_t n, stream_t s) {
+    return check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync D2D");
+}
+static void* malloc_async(size_t bytes, stream_t s) {
+    void* p = nullptr;
+    if (!check(cudaMallocAsync(&p, bytes, s), "cudaMallocAsync")) return nullptr;
+    return p;
+}
+static void free_async(void* p, stream_t s) { cudaFreeAsync(p, s); }
+static stream_t stream_create() {
+    cudaStream_t s = nullptr;
+    if (!check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
+    return s;
+}
+static void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
+static bool stream_sync(stream_t s) { return check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+
+}  // namespace rt
+}  // namespace b2
+
+#include "kernels.h"
+
+namespace b2 {
+namespace rt {
+
+template <class KT>
+static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
+    if (ctas == 0) return true;
+    if (ctas > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    // opt in to > 48 KiB dynamic shared memory once per (kernel, device)
+    static std::atomic<uint64_t> configured{0};
+    if (KT::SMEM_BYTES > 48 * 1024) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(configured.load(std::memory_order_acquire) & bit)) {
+            if (!check(cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+                       "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+                return false;
+            configured.fetch_or(bit, std::memory_order_release);
+        }
+    }
+    run_kernel<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
+}  // namespace rt
+}  // namespace b2
+
+#include "impl.inl"

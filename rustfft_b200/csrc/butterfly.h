@@ -1,0 +1,160 @@
+// In-register radix-R DFTs (forward sign, natural order in, natural order out).
+// These are the per-thread butterflies of the Stockham stages; the algorithm family is the
+// reference's (radix 2/4/8/16 for powers of two -- cf. src/algorithm/butterflies.rs Butterfly2/4/8/16
+// and radixn.rs butterfly_2..7 for 3/5/7) but the formulation is a plain DIT factorisation written
+// for FMA hardware, not a restatement of the reference's split-radix code.
+#pragma once
+#include "common.h"
+
+namespace b2 {
+
+template <typename T> struct K {
+    static constexpr T rsqrt2 = (T)0.70710678118654752440084436210484903928L;
+    static constexpr T c16_1 = (T)0.92387953251128675612818318939678828682L;  // cos(pi/8)
+    static constexpr T s16_1 = (T)0.38268343236508977172845998403039886676L;  // sin(pi/8)
+    // radix 3
+    static constexpr T c3 = (T)-0.5L;
+    static constexpr T s3 = (T)0.86602540378443864676372317075293618347L;  // sin(2pi/3)
+    // radix 5
+    static constexpr T c5_1 = (T)0.30901699437494742410229341718281905886L;   // cos(2pi/5)
+    static constexpr T c5_2 = (T)-0.80901699437494742410229341718281905886L;  // cos(4pi/5)
+    static constexpr T s5_1 = (T)0.95105651629515357211643933337938214340L;   // sin(2pi/5)
+    static constexpr T s5_2 = (T)0.58778525229247312916870595463907276860L;   // sin(4pi/5)
+    // radix 7
+    static constexpr T c7_1 = (T)0.62348980185873353052500488400423981063L;
+    static constexpr T c7_2 = (T)-0.22252093395631440428890256449679475947L;
+    static constexpr T c7_3 = (T)-0.90096886790241912623610231950744505117L;
+    static constexpr T s7_1 = (T)0.78183148246802980870844452667405775023L;
+    static constexpr T s7_2 = (T)0.97492791218182360701813168299393121723L;
+    static constexpr T s7_3 = (T)0.43388373911755812047576833284835875461L;
+};
+
+template <typename T> B2_HD void bf2(cx<T>& a, cx<T>& b) {
+    cx<T> t = a + b;
+    b = a - b;
+    a = t;
+}
+
+// v0..v3 natural in/out
+template <typename T> B2_HD void bf4(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3) {
+    cx<T> t0 = v0 + v2, t1 = v0 - v2, t2 = v1 + v3, t3 = mul_mi(v1 - v3);
+    v0 = t0 + t2;
+    v1 = t1 + t3;
+    v2 = t0 - t2;
+    v3 = t1 - t3;
+}
+
+template <typename T> B2_HD void bf3(cx<T>& v0, cx<T>& v1, cx<T>& v2) {
+    cx<T> s = v1 + v2, d = v1 - v2;
+    cx<T> m = mk<T>(v0.x + K<T>::c3 * s.x, v0.y + K<T>::c3 * s.y);
+    cx<T> r = mk<T>(K<T>::s3 * d.y, -K<T>::s3 * d.x);  // -i*s3*d
+    v0 = v0 + s;
+    v1 = m + r;
+    v2 = m - r;
+}
+
+template <typename T> B2_HD void bf5(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3, cx<T>& v4) {
+    cx<T> a = v1 + v4, b = v1 - v4, c = v2 + v3, d = v2 - v3;
+    cx<T> m1 = mk<T>(v0.x + K<T>::c5_1 * a.x + K<T>::c5_2 * c.x, v0.y + K<T>::c5_1 * a.y + K<T>::c5_2 * c.y);
+    cx<T> m2 = mk<T>(v0.x + K<T>::c5_2 * a.x + K<T>::c5_1 * c.x, v0.y + K<T>::c5_2 * a.y + K<T>::c5_1 * c.y);
+    // -i * (s1*b + s2*d) and -i * (s2*b - s1*d)
+    cx<T> q1 = mk<T>(K<T>::s5_1 * b.x + K<T>::s5_2 * d.x, K<T>::s5_1 * b.y + K<T>::s5_2 * d.y);
+    cx<T> q2 = mk<T>(K<T>::s5_2 * b.x - K<T>::s5_1 * d.x, K<T>::s5_2 * b.y - K<T>::s5_1 * d.y);
+    cx<T> r1 = mul_mi(q1), r2 = mul_mi(q2);
+    v0 = v0 + a + c;
+    v1 = m1 + r1;
+    v4 = m1 - r1;
+    v2 = m2 + r2;
+    v3 = m2 - r2;
+}
+
+template <typename T>
+B2_HD void bf7(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3, cx<T>& v4, cx<T>& v5, cx<T>& v6) {
+    cx<T> a1 = v1 + v6, b1 = v1 - v6, a2 = v2 + v5, b2 = v2 - v5, a3 = v3 + v4, b3 = v3 - v4;
+    const T c1 = K<T>::c7_1, c2 = K<T>::c7_2, c3 = K<T>::c7_3, s1 = K<T>::s7_1, s2 = K<T>::s7_2, s3 = K<T>::s7_3;
+    cx<T> m1 = mk<T>(v0.x + c1 * a1.x + c2 * a2.x + c3 * a3.x, v0.y + c1 * a1.y + c2 * a2.y + c3 * a3.y);
+    cx<T> m2 = mk<T>(v0.x + c2 * a1.x + c3 * a2.x + c1 * a3.x, v0.y + c2 * a1.y + c3 * a2.y + c1 * a3.y);
+    cx<T> m3 = mk<T>(v0.x + c3 * a1.x + c1 * a2.x + c2 * a3.x, v0.y + c3 * a1.y + c1 * a2.y + c2 * a3.y);
+    cx<T> q1 = mk<T>(s1 * b1.x + s2 * b2.x + s3 * b3.x, s1 * b1.y + s2 * b2.y + s3 * b3.y);
+    cx<T> q2 = mk<T>(s2 * b1.x - s3 * b2.x - s1 * b3.x, s2 * b1.y - s3 * b2.y - s1 * b3.y);
+    cx<T> q3 = mk<T>(s3 * b1.x - s1 * b2.x + s2 * b3.x, s3 * b1.y - s1 * b2.y + s2 * b3.y);
+    cx<T> r1 = mul_mi(q1), r2 = mul_mi(q2), r3 = mul_mi(q3);
+    v0 = v0 + a1 + a2 + a3;
+    v1 = m1 + r1;
+    v6 = m1 - r1;
+    v2 = m2 + r2;
+    v5 = m2 - r2;
+    v3 = m3 + r3;
+    v4 = m3 - r3;
+}
+
+// multiply by W8^1 = (1-i)/sqrt2 and W8^3 = (-1-i)/sqrt2
+template <typename T> B2_HD cx<T> mul_w8_1(cx<T> a) {
+    return mk<T>((a.x + a.y) * K<T>::rsqrt2, (a.y - a.x) * K<T>::rsqrt2);
+}
+template <typename T> B2_HD cx<T> mul_w8_3(cx<T> a) {
+    return mk<T>((a.y - a.x) * K<T>::rsqrt2, -(a.x + a.y) * K<T>::rsqrt2);
+}
+
+template <typename T> B2_HD void bf8(cx<T> (&v)[8]) {
+    // DIT: evens / odds 4-point, odd outputs twiddled by W8^k
+    bf4(v[0], v[2], v[4], v[6]);
+    bf4(v[1], v[3], v[5], v[7]);
+    cx<T> o1 = mul_w8_1(v[3]), o2 = mul_mi(v[5]), o3 = mul_w8_3(v[7]);
+    cx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+    v[0] = e0 + o0;
+    v[4] = e0 - o0;
+    v[1] = e1 + o1;
+    v[5] = e1 - o1;
+    v[2] = e2 + o2;
+    v[6] = e2 - o2;
+    v[3] = e3 + o3;
+    v[7] = e3 - o3;
+}
+
+template <typename T> B2_HD void bf16(cx<T> (&v)[16]) {
+    // n = 4*n1 + n2, k = k1 + 4*k2:  4-point over n1 for each n2, twiddle W16^(n2*k1), 4-point over n2
+    B2_UNROLL
+    for (int n2 = 0; n2 < 4; ++n2) bf4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);  // v[4*k1 + n2]
+    const cx<T> w1 = mk<T>(K<T>::c16_1, -K<T>::s16_1);  // W16^1
+    const cx<T> w3 = mk<T>(K<T>::s16_1, -K<T>::c16_1);  // W16^3
+    // k1 = 1: n2 = 1,2,3 -> W16^1, W16^2, W16^3
+    v[5] = cmul(v[5], w1);
+    v[6] = mul_w8_1(v[6]);
+    v[7] = cmul(v[7], w3);
+    // k1 = 2: W16^2, W16^4, W16^6
+    v[9] = mul_w8_1(v[9]);
+    v[10] = mul_mi(v[10]);
+    v[11] = mul_w8_3(v[11]);
+    // k1 = 3: W16^3, W16^6, W16^9 = -W16^1
+    v[13] = cmul(v[13], w3);
+    v[14] = mul_w8_3(v[14]);
+    v[15] = cmul(v[15], mk<T>(-K<T>::c16_1, K<T>::s16_1));
+    B2_UNROLL
+    for (int k1 = 0; k1 < 4; ++k1) bf4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> k2
+    // now v[4*k1 + k2] holds X[k1 + 4*k2]: transpose the 4x4 register tile to natural order
+    B2_UNROLL
+    for (int a = 0; a < 4; ++a) {
+        B2_UNROLL
+        for (int b = a + 1; b < 4; ++b) {
+            cx<T> t = v[4 * a + b];
+            v[4 * a + b] = v[4 * b + a];
+            v[4 * b + a] = t;
+        }
+    }
+}
+
+// dispatch on a register array
+template <int R, typename T> struct Bfly;
+template <typename T> struct Bfly<1, T> { static B2_HD void run(cx<T> (&)[1]) {} };
+template <typename T> struct Bfly<2, T> { static B2_HD void run(cx<T> (&v)[2]) { bf2(v[0], v[1]); } };
+template <typename T> struct Bfly<3, T> { static B2_HD void run(cx<T> (&v)[3]) { bf3(v[0], v[1], v[2]); } };
+template <typename T> struct Bfly<4, T> { static B2_HD void run(cx<T> (&v)[4]) { bf4(v[0], v[1], v[2], v[3]); } };
+template <typename T> struct Bfly<5, T> { static B2_HD void run(cx<T> (&v)[5]) { bf5(v[0], v[1], v[2], v[3], v[4]); } };
+template <typename T> struct Bfly<7, T> {
+    static B2_HD void run(cx<T> (&v)[7]) { bf7(v[0], v[1], v[2], v[3], v[4], v[5], v[6]); }
+};
+template <typename T> struct Bfly<8, T> { static B2_HD void run(cx<T> (&v)[8]) { bf8(v); } };
+template <typename T> struct Bfly<16, T> { static B2_HD void run(cx<T> (&v)[16]) { bf16(v); } };
+
+}  // namespace b2

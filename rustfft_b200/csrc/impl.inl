@@ -1,0 +1,619 @@
+// Host side of libb200fft: planner + C ABI, written against the small `rt::` runtime layer that the
+// including translation unit provides (b200fft.cu: CUDA runtime, sm_100a kernels;
+// tests/emu/b200fft_emu.cpp: a thread-by-thread CPU replay of the same kernel phases, test-only).
+//
+// Planner (what RustFFT's planners decide in src/plan.rs:412-665 / src/avx/avx_planner.rs:205-216,
+// re-decided for a GPU):
+//   len 0, 1                      -> Identity
+//   2^k <= DIRECT_MAX             -> Direct      one CTA pass, Stockham radix-4/8/16 in registers+smem
+//   2^k  > DIRECT_MAX (<= 2^20)   -> FourStep    two passes, intermediate kept in L2 by chunking
+//   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= DIRECT_MAX)
+//   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= DIRECT_MAX)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "host_math.h"
+#include "kernels.h"
+
+namespace b2 {
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// ---- geometry registry ---------------------------------------------------------------------
+template <typename T, int L> struct DirectGeo;  // whole transform per CTA pass, threads: j fastest
+template <typename T, int L> struct TileGeo;    // four-step tiles: F FFTs side by side
+
+#define B2_DIRECT(T, L, E, F, ...) \
+    template <> struct DirectGeo<T, L> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+#define B2_TILE(T, L, E, F, ...) \
+    template <> struct TileGeo<T, L> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+
+B2_DIRECT(float, 2, 2, 128, 2)
+B2_DIRECT(float, 4, 4, 128, 4)
+B2_DIRECT(float, 8, 8, 128, 8)
+B2_DIRECT(float, 16, 4, 32, 4, 4)
+B2_DIRECT(float, 32, 8, 32, 4, 8)
+B2_DIRECT(float, 64, 8, 16, 8, 8)
+B2_DIRECT(float, 128, 16, 16, 8, 16)
+B2_DIRECT(float, 256, 16, 8, 16, 16)
+B2_DIRECT(float, 512, 16, 8, 2, 16, 16)
+B2_DIRECT(float, 1024, 16, 4, 4, 16, 16)
+B2_DIRECT(float, 2048, 16, 2, 8, 16, 16)
+B2_DIRECT(float, 4096, 16, 1, 16, 16, 16)
+
+B2_DIRECT(double, 2, 2, 128, 2)
+B2_DIRECT(double, 4, 4, 128, 4)
+B2_DIRECT(double, 8, 8, 64, 8)
+B2_DIRECT(double, 16, 4, 32, 4, 4)
+B2_DIRECT(double, 32, 8, 32, 4, 8)
+B2_DIRECT(double, 64, 8, 16, 8, 8)
+B2_DIRECT(double, 128, 8, 8, 2, 8, 8)
+B2_DIRECT(double, 256, 8, 8, 4, 8, 8)
+B2_DIRECT(double, 512, 8, 4, 8, 8, 8)
+B2_DIRECT(double, 1024, 8, 2, 2, 8, 8, 8)
+B2_DIRECT(double, 2048, 8, 1, 4, 8, 8, 8)
+B2_DIRECT(double, 4096, 8, 1, 8, 8, 8, 8)
+
+B2_TILE(float, 64, 8, 16, 8, 8)
+B2_TILE(float, 128, 16, 16, 8, 16)
+B2_TILE(float, 256, 16, 16, 16, 16)
+B2_TILE(float, 512, 16, 16, 2, 16, 16)
+B2_TILE(float, 1024, 16, 8, 4, 16, 16)
+
+B2_TILE(double, 64, 8, 16, 8, 8)
+B2_TILE(double, 128, 8, 16, 2, 8, 8)
+B2_TILE(double, 256, 8, 8, 4, 8, 8)
+B2_TILE(double, 512, 8, 8, 8, 8, 8)
+B2_TILE(double, 1024, 8, 4, 2, 8, 8, 8)
+
+static constexpr uint32_t DIRECT_MAX = 4096;
+static constexpr uint32_t TILE_MIN = 64, TILE_MAX = 1024;
+
+// ---- plan object ----------------------------------------------------------------------------
+struct ExecCtx {
+    const void* in;
+    void* out;
+    void* work;
+    uint64_t batch;
+    rt::stream_t stream;
+};
+
+}  // namespace b2
+
+struct b200fft_plan {
+    uint64_t len = 0;
+    int direction = 0, precision = 0, device = 0;
+    std::string desc;
+    std::vector<void*> tables;  // device allocations owned by the plan
+    std::function<bool(const b2::ExecCtx&)> exec;
+    std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
+    std::function<uint64_t(uint64_t)> launches = [](uint64_t) { return (uint64_t)0; };
+    ~b200fft_plan() {
+        for (void* p : tables) b2::rt::dfree(p);
+    }
+};
+
+namespace b2 {
+
+template <class V>
+static const V* upload(b200fft_plan& pl, const std::vector<V>& host) {
+    if (host.empty()) return nullptr;
+    void* d = rt::dmalloc(host.size() * sizeof(V));
+    if (!d) return nullptr;
+    pl.tables.push_back(d);
+    if (!rt::h2d_sync(d, host.data(), host.size() * sizeof(V))) return nullptr;
+    return reinterpret_cast<const V*>(d);
+}
+
+// packed stage twiddles of a geometry: stage s >= 1, layout [(r-1)*p + k] = W_{pR}^{k r}
+template <class G>
+static std::vector<cx<typename G::T>> stage_twiddles() {
+    using T = typename G::T;
+    using RL = typename G::RL;
+    std::vector<cx<T>> tw((size_t)RL::tw_total());
+    int p = RL::get(0);
+    for (int s = 1; s < RL::N; ++s) {
+        const int R = RL::get(s);
+        const int off = RL::tw_offset(s);
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < p; ++k) tw[(size_t)off + (size_t)(r - 1) * p + k] = hm::twiddle<T>((uint64_t)k * r, (uint64_t)p * R);
+        p *= R;
+    }
+    return tw;
+}
+
+static uint64_t chunk_bytes() {
+    // target footprint of the L2-resident intermediate of multi-pass plans (B200 L2: ~126 MB)
+    static uint64_t v = [] {
+        const char* e = std::getenv("B200FFT_CHUNK_MB");
+        uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 32;
+        if (mb < 1) mb = 1;
+        return mb << 20;
+    }();
+    return v;
+}
+
+template <typename T>
+struct Builder {
+    typedef cx<T> C;
+
+    // ---------------- Direct ----------------
+    template <int L, bool SW>
+    static bool make_direct_t(b200fft_plan& pl) {
+        using G = typename DirectGeo<T, L>::type;
+        using KT = FftKernel<G, JF, JF, LoadRows<T, SW>, StoreRows<T, SW>>;
+        const C* tw = nullptr;
+        if (G::TW_ELEMS) {
+            tw = upload(pl, stage_twiddles<G>());
+            if (!tw) return false;
+        }
+        pl.exec = [tw](const ExecCtx& c) {
+            typename KT::Params p;
+            p.load = LoadRows<T, SW>{(const C*)c.in, (uint32_t)L};
+            p.store = StoreRows<T, SW>{(C*)c.out, (uint32_t)L};
+            p.tw = tw;
+            p.n_fft = c.batch;
+            return rt::launch<KT>(p, (c.batch + G::F - 1) / G::F, c.stream);
+        };
+        pl.launches = [](uint64_t) { return (uint64_t)1; };
+        pl.desc = "Direct{" + std::to_string(L) + "}";
+        return true;
+    }
+    template <int L>
+    static bool make_direct(b200fft_plan& pl) {
+        return pl.direction ? make_direct_t<L, true>(pl) : make_direct_t<L, false>(pl);
+    }
+    static bool make_direct_rt(b200fft_plan& pl, uint32_t L) {
+        switch (L) {
+            case 2: return make_direct<2>(pl);
+            case 4: return make_direct<4>(pl);
+            case 8: return make_direct<8>(pl);
+            case 16: return make_direct<16>(pl);
+            case 32: return make_direct<32>(pl);
+            case 64: return make_direct<64>(pl);
+            case 128: return make_direct<128>(pl);
+            case 256: return make_direct<256>(pl);
+            case 512: return make_direct<512>(pl);
+            case 1024: return make_direct<1024>(pl);
+            case 2048: return make_direct<2048>(pl);
+            case 4096: return make_direct<4096>(pl);
+        }
+        return false;
+    }
+
+    // ---------------- FourStep ----------------
+    // N = N1*N2.  pass A: N2 strided columns, N1-point FFT each, times W_N^(n2 k1), written to the
+    // workspace in the same [k1][n2] layout; pass B: N1 contiguous rows, N2-point FFT each, written
+    // transposed: X[k1 + N1 k2].  Chunked over the batch so the workspace stays L2 resident.
+    struct PassFns {
+        std::function<bool(const C* in, C* work, uint64_t nb, rt::stream_t)> a;
+        std::function<bool(const C* work, C* out, uint64_t nb, rt::stream_t)> b;
+    };
+    template <int L1, bool SW>
+    static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, TwoLevelTw<T> tl, PassFns& fns) {
+        using G = typename TileGeo<T, L1>::type;
+        using KT = FftKernel<G, FF, FF, LoadCols<T, SW>, StoreColsTw<T>>;
+        const C* tw = upload(pl, stage_twiddles<G>());
+        if (!tw) return false;
+        fns.a = [=](const C* in, C* work, uint64_t nb, rt::stream_t s) {
+            typename KT::Params p;
+            p.load = LoadCols<T, SW>{in, lgN, lg2};
+            p.store = StoreColsTw<T>{work, lgN, lg2, tl};
+            p.tw = tw;
+            p.n_fft = nb << lg2;
+            return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
+        };
+        return true;
+    }
+    template <int L2, bool SW>
+    static bool make_pass_b(b200fft_plan& pl, uint32_t lgN, uint32_t lg1, PassFns& fns) {
+        using G = typename TileGeo<T, L2>::type;
+        using KT = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposed<T, SW>>;
+        const C* tw = upload(pl, stage_twiddles<G>());
+        if (!tw) return false;
+        fns.b = [=](const C* work, C* out, uint64_t nb, rt::stream_t s) {
+            typename KT::Params p;
+            p.load = LoadRows<T, false>{work, (uint32_t)L2};
+            p.store = StoreTransposed<T, SW>{out, lgN, lg1};
+            p.tw = tw;
+            p.n_fft = nb << lg1;
+            return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
+        };
+        return true;
+    }
+    template <bool SW>
+    static bool make_pass_a_rt(b200fft_plan& pl, uint32_t L1, uint32_t lgN, uint32_t lg2, TwoLevelTw<T> tl, PassFns& f) {
+        switch (L1) {
+            case 64: return make_pass_a<64, SW>(pl, lgN, lg2, tl, f);
+            case 128: return make_pass_a<128, SW>(pl, lgN, lg2, tl, f);
+            case 256: return make_pass_a<256, SW>(pl, lgN, lg2, tl, f);
+            case 512: return make_pass_a<512, SW>(pl, lgN, lg2, tl, f);
+            case 1024: return make_pass_a<1024, SW>(pl, lgN, lg2, tl, f);
+        }
+        return false;
+    }
+    template <bool SW>
+    static bool make_pass_b_rt(b200fft_plan& pl, uint32_t L2, uint32_t lgN, uint32_t lg1, PassFns& f) {
+        switch (L2) {
+            case 64: return make_pass_b<64, SW>(pl, lgN, lg1, f);
+            case 128: return make_pass_b<128, SW>(pl, lgN, lg1, f);
+            case 256: return make_pass_b<256, SW>(pl, lgN, lg1, f);
+            case 512: return make_pass_b<512, SW>(pl, lgN, lg1, f);
+            case 1024: return make_pass_b<1024, SW>(pl, lgN, lg1, f);
+        }
+        return false;
+    }
+    static bool make_two_level(b200fft_plan& pl, uint32_t lgN, TwoLevelTw<T>& tl) {
+        const uint32_t lgS = (lgN + 1) / 2;
+        const uint64_t N = 1ull << lgN, S = 1ull << lgS;
+        std::vector<C> a((size_t)S), b((size_t)(N >> lgS));
+        for (uint64_t i = 0; i < S; ++i) a[(size_t)i] = hm::twiddle<T>(i, N);
+        for (uint64_t i = 0; i < (N >> lgS); ++i) b[(size_t)i] = hm::twiddle<T>(i << lgS, N);
+        tl.a = upload(pl, a);
+        tl.b = upload(pl, b);
+        tl.lgS = lgS;
+        return tl.a && tl.b;
+    }
+    static bool make_four_step(b200fft_plan& pl, uint32_t lgN) {
+        const uint32_t lg1 = lgN / 2, lg2 = lgN - lg1;  // N1 <= N2
+        const uint32_t N1 = 1u << lg1, N2 = 1u << lg2;
+        if (N1 < TILE_MIN || N2 > TILE_MAX) return false;
+        TwoLevelTw<T> tl;
+        if (!make_two_level(pl, lgN, tl)) return false;
+        PassFns fns;
+        const bool sw = pl.direction != 0;
+        const bool ok_a = sw ? make_pass_a_rt<true>(pl, N1, lgN, lg2, tl, fns) : make_pass_a_rt<false>(pl, N1, lgN, lg2, tl, fns);
+        const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, fns);
+        if (!ok_a || !ok_b) return false;
+        const uint64_t N = 1ull << lgN;
+        const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / (N * sizeof(C)));
+        pl.work_bytes = [=](uint64_t batch) { return std::min(batch, chunk) * N * sizeof(C); };
+        pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+        pl.exec = [=](const ExecCtx& c) {
+            const C* in = (const C*)c.in;
+            C* out = (C*)c.out;
+            C* work = (C*)c.work;
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                if (!fns.a(in + b0 * N, work, nb, c.stream)) return false;
+                if (!fns.b(work, out + b0 * N, nb, c.stream)) return false;
+            }
+            return true;
+        };
+        pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        return true;
+    }
+
+    // ---------------- Bluestein (fused) ----------------
+    static void bluestein_tables(uint64_t n, uint64_t M, std::vector<C>& chirp, std::vector<C>& mult) {
+        chirp.resize((size_t)n);
+        std::vector<hm::cld> c((size_t)M, hm::cld{0, 0});
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t m = (uint64_t)(((unsigned __int128)i * i) % (2 * n));
+            const hm::cld w = hm::twiddle_ld(m, 2 * n);  // forward chirp W_2n^(i^2)
+            chirp[(size_t)i] = mk<T>((T)w.x, (T)w.y);
+            const hm::cld cj{w.x / (hm::ld)M, -w.y / (hm::ld)M};  // conj(w)/M
+            c[(size_t)i] = cj;
+            if (i) c[(size_t)(M - i)] = cj;
+        }
+        hm::fft_pow2_ld(c);
+        mult.resize((size_t)M);
+        for (uint64_t i = 0; i < M; ++i) mult[(size_t)i] = mk<T>((T)c[(size_t)i].x, (T)c[(size_t)i].y);
+    }
+    template <int M, bool SW>
+    static bool make_bluestein_t(b200fft_plan& pl) {
+        using G = typename DirectGeo<T, M>::type;
+        using KT = BluesteinKernel<G, SW>;
+        const uint32_t n = (uint32_t)pl.len;
+        std::vector<C> chirp, mult;
+        bluestein_tables(n, M, chirp, mult);
+        const C* d_chirp = upload(pl, chirp);
+        const C* d_mult = upload(pl, mult);
+        const C* tw = G::TW_ELEMS ? upload(pl, stage_twiddles<G>()) : nullptr;
+        if (!d_chirp || !d_mult || (G::TW_ELEMS && !tw)) return false;
+        pl.exec = [=](const ExecCtx& c) {
+            typename KT::Params p;
+            p.in = (const C*)c.in;
+            p.out = (C*)c.out;
+            p.chirp = d_chirp;
+            p.mult = d_mult;
+            p.tw = tw;
+            p.n = n;
+            p.n_fft = c.batch;
+            return rt::launch<KT>(p, (c.batch + G::F - 1) / G::F, c.stream);
+        };
+        pl.launches = [](uint64_t) { return (uint64_t)1; };
+        pl.desc = "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",fused}";
+        return true;
+    }
+    template <int M>
+    static bool make_bluestein(b200fft_plan& pl) {
+        return pl.direction ? make_bluestein_t<M, true>(pl) : make_bluestein_t<M, false>(pl);
+    }
+    static bool make_bluestein_rt(b200fft_plan& pl, uint32_t M) {
+        switch (M) {
+            case 8: return make_bluestein<8>(pl);
+            case 16: return make_bluestein<16>(pl);
+            case 32: return make_bluestein<32>(pl);
+            case 64: return make_bluestein<64>(pl);
+            case 128: return make_bluestein<128>(pl);
+            case 256: return make_bluestein<256>(pl);
+            case 512: return make_bluestein<512>(pl);
+            case 1024: return make_bluestein<1024>(pl);
+            case 2048: return make_bluestein<2048>(pl);
+            case 4096: return make_bluestein<4096>(pl);
+        }
+        return false;
+    }
+
+    // ---------------- Rader (fused) ----------------
+    template <int M, bool SW>
+    static bool make_rader_t(b200fft_plan& pl) {
+        using G = typename DirectGeo<T, M>::type;
+        using KT = RaderKernel<G, SW>;
+        const uint64_t n = pl.len;
+        const uint64_t g = hm::primitive_root(n);
+        const uint64_t gi = hm::powmod(g, n - 2, n);
+        std::vector<uint32_t> gpow((size_t)M), ginv((size_t)M);
+        std::vector<hm::cld> d((size_t)M);
+        uint64_t a = 1, b = 1;
+        for (uint64_t i = 0; i < (uint64_t)M; ++i) {
+            // d[i] = twiddle(g^-i mod n, n) / M   (b = g^-i before the update)
+            const hm::cld w = hm::twiddle_ld(b, n);
+            d[(size_t)i] = hm::cld{w.x / (hm::ld)M, w.y / (hm::ld)M};
+            a = hm::mulmod(a, g, n);
+            b = hm::mulmod(b, gi, n);
+            gpow[(size_t)i] = (uint32_t)a;  // g^(i+1)
+            ginv[(size_t)i] = (uint32_t)b;  // g^-(i+1)
+        }
+        hm::fft_pow2_ld(d);
+        std::vector<C> mult((size_t)M);
+        for (size_t i = 0; i < (size_t)M; ++i) mult[i] = mk<T>((T)d[i].x, (T)d[i].y);
+        const uint32_t* d_gpow = upload(pl, gpow);
+        const uint32_t* d_ginv = upload(pl, ginv);
+        const C* d_mult = upload(pl, mult);
+        const C* tw = G::TW_ELEMS ? upload(pl, stage_twiddles<G>()) : nullptr;
+        if (!d_gpow || !d_ginv || !d_mult || (G::TW_ELEMS && !tw)) return false;
+        pl.exec = [=](const ExecCtx& c) {
+            typename KT::Params p;
+            p.in = (const C*)c.in;
+            p.out = (C*)c.out;
+            p.gpow = d_gpow;
+            p.ginv = d_ginv;
+            p.mult = d_mult;
+            p.tw = tw;
+            p.n = (uint32_t)n;
+            p.n_fft = c.batch;
+            return rt::launch<KT>(p, (c.batch + G::F - 1) / G::F, c.stream);
+        };
+        pl.launches = [](uint64_t) { return (uint64_t)1; };
+        pl.desc = "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(g) + ",fused}";
+        return true;
+    }
+    template <int M>
+    static bool make_rader(b200fft_plan& pl) {
+        return pl.direction ? make_rader_t<M, true>(pl) : make_rader_t<M, false>(pl);
+    }
+    static bool make_rader_rt(b200fft_plan& pl, uint32_t M) {
+        switch (M) {
+            case 2: return make_rader<2>(pl);
+            case 4: return make_rader<4>(pl);
+            case 16: return make_rader<16>(pl);
+            case 256: return make_rader<256>(pl);
+        }
+        return false;
+    }
+
+    // ---------------- top level ----------------
+    static int build(b200fft_plan& pl) {
+        const uint64_t n = pl.len;
+        if (n <= 1) {
+            pl.exec = [n](const ExecCtx& c) {
+                if (n == 0 || c.in == c.out || c.batch == 0) return true;
+                return rt::d2d_async(c.out, c.in, c.batch * n * sizeof(C), c.stream);
+            };
+            pl.desc = "Identity{" + std::to_string(n) + "}";
+            return B200FFT_OK;
+        }
+        bool ok = false;
+        if (hm::is_pow2(n)) {
+            if (n <= DIRECT_MAX)
+                ok = make_direct_rt(pl, (uint32_t)n);
+            else if (n <= (uint64_t)TILE_MAX * TILE_MAX)
+                ok = make_four_step(pl, hm::ilog2(n));
+            else
+                return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^20 are not planned by this build");
+        } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
+            ok = make_rader_rt(pl, (uint32_t)(n - 1));
+        } else {
+            const uint64_t M = hm::next_pow2(2 * n - 1);
+            if (M <= DIRECT_MAX)
+                ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
+            else
+                return fail(B200FFT_ERR_UNSUPPORTED,
+                            "non-power-of-two lengths above " + std::to_string(DIRECT_MAX / 2) + " are not planned by this build");
+        }
+        if (!ok) return fail(B200FFT_ERR_CUDA, "plan construction failed: " + rt::last_error());
+        return B200FFT_OK;
+    }
+};
+
+static int validate_len(const b200fft_plan* pl, uint64_t n_in, uint64_t n_out, bool two) {
+    // src/common.rs:13-104 (messages kept verbatim; the Rust shim panics with them)
+    const uint64_t len = pl->len;
+    if (two && n_in != n_out)
+        return fail(B200FFT_ERR_LEN_MISMATCH,
+                    "Provided FFT input buffer and output buffer must have the same length. Got input.len() = " +
+                        std::to_string(n_in) + ", output.len() = " + std::to_string(n_out));
+    if (n_in < len)
+        return fail(B200FFT_ERR_BUFFER_TOO_SMALL, "Provided FFT buffer was too small. Expected len = " +
+                                                      std::to_string(len) + ", got len = " + std::to_string(n_in));
+    if (n_in % len != 0)
+        return fail(B200FFT_ERR_NOT_MULTIPLE, "Input FFT buffer must be a multiple of FFT length. Expected multiple of " +
+                                                  std::to_string(len) + ", got len = " + std::to_string(n_in));
+    return B200FFT_OK;
+}
+
+static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_out, uint64_t batch, rt::stream_t stream,
+                            void* ws, uint64_t ws_bytes, bool ws_given) {
+    if (!pl || (!d_in && batch && pl->len) || (!d_out && batch && pl->len)) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    if (pl->len == 0 || batch == 0) return B200FFT_OK;  // src/fft_helper.rs:16-18
+    if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    const uint64_t need = pl->work_bytes(batch);
+    void* work = ws;
+    bool own = false;
+    if (need) {
+        if (ws_given) {
+            if (ws_bytes < need || !ws)
+                return fail(B200FFT_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+        } else {
+            work = rt::malloc_async(need, stream);
+            if (!work) return fail(B200FFT_ERR_CUDA, "workspace allocation failed: " + rt::last_error());
+            own = true;
+        }
+    }
+    ExecCtx c{d_in, d_out, work, batch, stream};
+    const bool ok = pl->exec(c);
+    if (own) rt::free_async(work, stream);
+    if (!ok) return fail(B200FFT_ERR_CUDA, "kernel launch failed: " + rt::last_error());
+    return B200FFT_OK;
+}
+
+// Host-slice path: chunks of the batch flow H2D -> kernels -> D2H on two streams with two device
+// buffers, so copies in both directions overlap compute when the caller's memory is pinned.
+static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
+    if (!pl) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    if (pl->len == 0 || n_complex == 0) return B200FFT_OK;
+    if (!in || !out) return fail(B200FFT_ERR_INVALID_ARG, "null buffer");
+    if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
+    const uint64_t batch = n_complex / pl->len;
+    const uint64_t tbytes = pl->len * esz;
+    uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / tbytes);
+    if (chunk > batch) chunk = batch;
+    const int NBUF = 2;
+    void* dbuf[NBUF] = {nullptr, nullptr};
+    void* wbuf[NBUF] = {nullptr, nullptr};
+    rt::stream_t st[NBUF] = {nullptr, nullptr};
+    const uint64_t wbytes = pl->work_bytes(chunk);
+    int rc = B200FFT_OK;
+    for (int i = 0; i < NBUF && rc == B200FFT_OK; ++i) {
+        st[i] = rt::stream_create();
+        dbuf[i] = rt::dmalloc(chunk * tbytes);
+        if (wbytes) wbuf[i] = rt::dmalloc(wbytes);
+        if (!st[i] || !dbuf[i] || (wbytes && !wbuf[i])) rc = fail(B200FFT_ERR_CUDA, "staging allocation failed: " + rt::last_error());
+    }
+    uint64_t idx = 0;
+    for (uint64_t b0 = 0; b0 < batch && rc == B200FFT_OK; b0 += chunk, ++idx) {
+        const int s = (int)(idx % NBUF);
+        const uint64_t nb = std::min(chunk, batch - b0);
+        const char* src = (const char*)in + b0 * tbytes;
+        char* dst = (char*)out + b0 * tbytes;
+        if (!rt::h2d_async(dbuf[s], src, nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
+        rc = exec_device_impl(pl, dbuf[s], dbuf[s], nb, st[s], wbuf[s], wbytes, wbytes != 0);
+        if (rc != B200FFT_OK) break;
+        if (!rt::d2h_async(dst, dbuf[s], nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        if (st[i] && !rt::stream_sync(st[i]) && rc == B200FFT_OK) rc = fail(B200FFT_ERR_CUDA, rt::last_error());
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        if (dbuf[i]) rt::dfree(dbuf[i]);
+        if (wbuf[i]) rt::dfree(wbuf[i]);
+        if (st[i]) rt::stream_destroy(st[i]);
+    }
+    return rc;
+}
+
+}  // namespace b2
+
+extern "C" {
+
+int b200fft_device_count(int* n) {
+    if (!n) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    *n = b2::rt::device_count();
+    return B200FFT_OK;
+}
+
+int b200fft_plan_create(b200fft_plan** out, uint64_t len, int direction, int precision, int device) {
+    if (!out) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if ((direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) || (precision != B200FFT_F32 && precision != B200FFT_F64))
+        return b2::fail(B200FFT_ERR_INVALID_ARG, "unknown direction or precision");
+    const int ndev = b2::rt::device_count();
+    if (ndev <= 0) return b2::fail(B200FFT_ERR_NO_DEVICE, "no sm_100 CUDA device is visible (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return b2::fail(B200FFT_ERR_INVALID_ARG, "device index out of range");
+    if (!b2::rt::set_device(device)) return b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    std::unique_ptr<b200fft_plan> pl(new b200fft_plan());
+    pl->len = len;
+    pl->direction = direction;
+    pl->precision = precision;
+    pl->device = device;
+    const int rc = precision == B200FFT_F32 ? b2::Builder<float>::build(*pl) : b2::Builder<double>::build(*pl);
+    if (rc != B200FFT_OK) return rc;
+    *out = pl.release();
+    return B200FFT_OK;
+}
+
+int b200fft_plan_destroy(b200fft_plan* plan) {
+    if (!plan) return B200FFT_OK;
+    b2::rt::set_device(plan->device);
+    delete plan;
+    return B200FFT_OK;
+}
+
+uint64_t b200fft_plan_len(const b200fft_plan* plan) { return plan ? plan->len : 0; }
+int b200fft_plan_direction(const b200fft_plan* plan) { return plan ? plan->direction : -1; }
+int b200fft_plan_precision(const b200fft_plan* plan) { return plan ? plan->precision : -1; }
+uint64_t b200fft_plan_scratch_len(const b200fft_plan*, int) { return 0; }
+uint64_t b200fft_plan_launches(const b200fft_plan* plan, uint64_t batch) { return plan ? plan->launches(batch) : 0; }
+
+int b200fft_plan_describe(const b200fft_plan* plan, char* buf, uint64_t cap) {
+    if (!plan || !buf || cap == 0) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    if (plan->desc.size() + 1 > cap) return b2::fail(B200FFT_ERR_INVALID_ARG, "buffer too small");
+    std::memcpy(buf, plan->desc.c_str(), plan->desc.size() + 1);
+    return (int)plan->desc.size();
+}
+
+int b200fft_exec_host_inplace(const b200fft_plan* plan, void* buffer, uint64_t n_complex) {
+    if (!plan) return b2::fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    if (plan->len == 0) return B200FFT_OK;
+    const int v = b2::validate_len(plan, n_complex, n_complex, false);
+    if (v != B200FFT_OK) return v;
+    return b2::exec_host_impl(plan, buffer, buffer, n_complex);
+}
+
+int b200fft_exec_host_outofplace(const b200fft_plan* plan, const void* input, void* output, uint64_t n_complex) {
+    if (!plan) return b2::fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    if (plan->len == 0) return B200FFT_OK;
+    const int v = b2::validate_len(plan, n_complex, n_complex, true);
+    if (v != B200FFT_OK) return v;
+    return b2::exec_host_impl(plan, input, output, n_complex);
+}
+
+int b200fft_exec_device(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream) {
+    return b2::exec_device_impl(plan, d_in, d_out, batch, (b2::rt::stream_t)cuda_stream, nullptr, 0, false);
+}
+
+uint64_t b200fft_workspace_bytes(const b200fft_plan* plan, uint64_t batch) { return plan ? plan->work_bytes(batch) : 0; }
+
+int b200fft_exec_device_ws(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream,
+                           void* d_workspace, uint64_t workspace_bytes) {
+    return b2::exec_device_impl(plan, d_in, d_out, batch, (b2::rt::stream_t)cuda_stream, d_workspace, workspace_bytes, true);
+}
+
+const char* b200fft_last_error(void) { return b2::g_last_error.c_str(); }
+const char* b200fft_version(void) { return "b200fft 0.1 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// Kernel bodies (phase functions) built on the CTA engine, and the global-memory functors that
+// give each its role:
+//
+//   FftKernel<G, M0, M1, Load, Store>   one FFT pass: Load -> L-point FFT -> Store
+//       Load = LoadRows,  Store = StoreRows            whole transform in one CTA pass  (N = L)
+//       Load = LoadCols,  Store = StoreColsTw          four-step pass A: strided column FFTs of
+//                                                      length N1, times W_N^(n2*k1), in place
+//       Load = LoadRows,  Store = StoreTransposed      four-step pass B: contiguous row FFTs of
+//                                                      length N2, written back transposed
+//   (four-step == the reference's six-step MixedRadix, src/algorithm/mixed_radix.rs:128-158, with
+//    its three transposes folded into the strided loads/stores of the two passes)
+//
+//   BluesteinKernel<G>   whole chirp-z transform of one signal in one CTA pass
+//                        (src/algorithm/bluesteins_algorithm.rs:100-136 fused: x*w -> FFT_M ->
+//                         *C, conj -> FFT_M -> conj * w)
+//   RaderKernel<G>       whole Rader transform of one prime-length signal in one CTA pass
+//                        (src/algorithm/raders_algorithm.rs:235-283 fused)
+//
+// Direction: every table is "forward".  An inverse plan sets SWAP on the outermost load and the
+// outermost store (ifft(x) = swap(fft(swap(x))), swap = exchange re/im) -- see common.h.
+#pragma once
+#include "engine.h"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------
+// Functors.  prep(g, ok) is evaluated once per thread (g = global FFT index of this thread's
+// FFT, ok = g is inside the launch), get/put once per element.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SWAP>
+struct LoadRows {  // element e of FFT g at in[g*len + e]
+    const cx<T>* in;
+    uint32_t len;
+    struct St { const cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const { return St{in + g * (uint64_t)len, ok}; }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        cx<T> v = ld_stream(s.p + e);
+        return SWAP ? swap_ri(v) : v;
+    }
+};
+
+template <typename T, bool SWAP>
+struct StoreRows {
+    cx<T>* out;
+    uint32_t len;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const { return St{out + g * (uint64_t)len, ok}; }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) st_stream(s.p + e, SWAP ? swap_ri(v) : v);
+    }
+};
+
+// four-step pass A load: FFT g = (transform b, column c) with g = b*N2 + c; element e (= n1) lives
+// at in[b*N + e*N2 + c].  N2 = 1 << lg2.
+template <typename T, bool SWAP>
+struct LoadCols {
+    const cx<T>* in;
+    uint32_t lgN;   // log2 N
+    uint32_t lg2;   // log2 N2
+    struct St { const cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg2, c = g & ((1ull << lg2) - 1);
+        return St{in + (b << lgN) + c, ok};
+    }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        cx<T> v = ld_stream(s.p + ((uint32_t)e << lg2));
+        return SWAP ? swap_ri(v) : v;
+    }
+};
+
+// two-level twiddle W_N^m = A[m & (S-1)] * B[m >> lgS]: both tables are rounded from a
+// long-double evaluation, so the product carries <= 1.5 ulp instead of a table of N entries per
+// size (for N = 2^20 that table alone would be 8 MiB of L2 traffic per pass)
+template <typename T>
+struct TwoLevelTw {
+    const cx<T>* a;  // W_N^i,        i < S = 1 << lgS
+    const cx<T>* b;  // W_N^(S*i),    i < N / S
+    uint32_t lgS;
+    B2_HD cx<T> at(uint32_t m) const {
+        const cx<T> lo = ldg(a + (m & ((1u << lgS) - 1)));
+        const cx<T> hi = ldg(b + (m >> lgS));
+        return cmul(lo, hi);
+    }
+};
+
+// four-step pass A store: out[b*N + k1*N2 + c] = v * W_N^(c*k1)   (same slots the tile was read
+// from, so the pass is in place per tile; plain write-back stores: the next pass re-reads from L2)
+template <typename T>
+struct StoreColsTw {
+    cx<T>* out;
+    uint32_t lgN, lg2;
+    TwoLevelTw<T> tw;
+    struct St { cx<T>* p; uint32_t c; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg2, c = g & ((1ull << lg2) - 1);
+        return St{out + (b << lgN) + c, (uint32_t)c, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (!s.ok) return;
+        s.p[(uint32_t)e << lg2] = cmul(v, tw.at(s.c * (uint32_t)e));
+    }
+};
+
+// four-step pass B store: FFT g = (transform b, row k1), g = b*N1 + k1; output k2 (= e) goes to
+// out[b*N + k1 + N1*e].  N1 = 1 << lg1.
+template <typename T, bool SWAP>
+struct StoreTransposed {
+    cx<T>* out;
+    uint32_t lgN, lg1;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg1, k1 = g & ((1ull << lg1) - 1);
+        return St{out + (b << lgN) + k1, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) st_stream(s.p + ((uint32_t)e << lg1), SWAP ? swap_ri(v) : v);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+template <class G, Map M0, Map M1, class Load, class Store>
+struct FftKernel {
+    using T = typename G::T;
+    using Eng = Engine<G, M0, M1>;
+    static constexpr int NT = G::NT;
+    static constexpr int NPHASE = Eng::NPHASE;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
+    struct Params {
+        Load load;
+        Store store;
+        const cx<T>* tw;   // packed stage twiddles, RL::tw_total() entries
+        uint64_t n_fft;    // FFTs in this launch
+    };
+    struct Regs { cx<T> v[G::E]; };
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs& r, cx<T>* smem) {
+        if constexpr (P == 0) {
+            int f, j;
+            Eng::template owner<0>(tid, f, j);
+            const uint64_t g = (uint64_t)bid * G::F + f;
+            const auto st = p.load.prep(g, g < p.n_fft);
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) r.v[q] = p.load.get(st, j + G::TP * q);
+        }
+        Eng::template phase<P>(tid, r.v, smem, p.tw);
+        if constexpr (P == NPHASE - 1) {
+            int f, j;
+            Eng::out_owner(tid, f, j);
+            const uint64_t g = (uint64_t)bid * G::F + f;
+            const auto st = p.store.prep(g, g < p.n_fft);
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) p.store.put(st, j + G::TP * q, r.v[q]);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Bluestein, fully fused (M = G::L >= 2n-1).  chirp[i] = W_2n^(i^2 mod 2n) (src/twiddles.rs:25-57),
+// mult = FFT_M of the wrapped conjugate chirp / M (src/algorithm/bluesteins_algorithm.rs:62-83).
+// ------------------------------------------------------------------------------------------
+template <class G, bool SWAP>
+struct BluesteinKernel {
+    using T = typename G::T;
+    using Eng = Engine<G, JF, JF>;
+    static constexpr int NT = G::NT;
+    static constexpr int NP1 = Eng::NPHASE;
+    static constexpr int NPHASE = 2 * NP1 - 1;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
+    struct Params {
+        const cx<T>* in;
+        cx<T>* out;
+        const cx<T>* chirp;  // n entries
+        const cx<T>* mult;   // M entries
+        const cx<T>* tw;     // stage twiddles of the M-point FFT
+        uint32_t n;
+        uint64_t n_fft;
+    };
+    struct Regs { cx<T> v[G::E]; };
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs& r, cx<T>* smem) {
+        int f, j;
+        tid_to_fj<G, JF>(tid, f, j);
+        const uint64_t g = (uint64_t)bid * G::F + f;
+        const bool ok = g < p.n_fft;
+        if constexpr (P == 0) {
+            const cx<T>* src = p.in + g * (uint64_t)p.n;
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                cx<T> v = mk<T>(0, 0);
+                if (ok && e < p.n) {
+                    v = ld_stream(src + e);
+                    if (SWAP) v = swap_ri(v);
+                    v = cmul(v, ldg(p.chirp + e));
+                }
+                r.v[q] = v;
+            }
+        }
+        if constexpr (P < NP1) {
+            Eng::template phase<P>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P == NP1 - 1) {
+            // pointwise multiply + conjugate, then stage 0 of the second FFT straight from registers
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                r.v[q] = conj(cmul(r.v[q], ldg(p.mult + e)));
+            }
+            Eng::template phase<0>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P >= NP1) {
+            Eng::template phase<P - NP1 + 1>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P == NPHASE - 1) {
+            cx<T>* dst = p.out + g * (uint64_t)p.n;
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                if (ok && e < p.n) {
+                    cx<T> v = cmul(conj(r.v[q]), ldg(p.chirp + e));
+                    st_stream(dst + e, SWAP ? swap_ri(v) : v);
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Rader, fully fused: prime length n = M + 1, M = G::L.
+//   a[i] = x[gpow[i]]  (gpow[i] = g^(i+1) mod n);  A = FFT_M a;  X[0] = x0 + A[0];
+//   b = conj(A .* D);  b[0] += conj(x0);  B = FFT_M b;  X[ginv[i]] = conj(B[i])
+// (src/algorithm/raders_algorithm.rs:235-283; D = FFT_M(twiddle(g^-i)/M), :86-109)
+// ------------------------------------------------------------------------------------------
+template <class G, bool SWAP>
+struct RaderKernel {
+    using T = typename G::T;
+    using Eng = Engine<G, JF, JF>;
+    static constexpr int NT = G::NT;
+    static constexpr int NP1 = Eng::NPHASE;
+    static constexpr int NPHASE = 2 * NP1 - 1;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
+    struct Params {
+        const cx<T>* in;
+        cx<T>* out;
+        const uint32_t* gpow;  // M entries: g^(i+1) mod n
+        const uint32_t* ginv;  // M entries: g^-(i+1) mod n
+        const cx<T>* mult;     // M entries (D)
+        const cx<T>* tw;
+        uint32_t n;
+        uint64_t n_fft;
+    };
+    struct Regs { cx<T> v[G::E]; cx<T> x0; };
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs& r, cx<T>* smem) {
+        int f, j;
+        tid_to_fj<G, JF>(tid, f, j);
+        const uint64_t g = (uint64_t)bid * G::F + f;
+        const bool ok = g < p.n_fft;
+        if constexpr (P == 0) {
+            const cx<T>* src = p.in + g * (uint64_t)p.n;
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                cx<T> v = mk<T>(0, 0);
+                if (ok) {
+                    v = src[ldg_u32(p.gpow + e)];
+                    if (SWAP) v = swap_ri(v);
+                }
+                r.v[q] = v;
+            }
+            r.x0 = mk<T>(0, 0);
+            if (ok && j == 0) {
+                r.x0 = src[0];
+                if (SWAP) r.x0 = swap_ri(r.x0);
+            }
+        }
+        if constexpr (P < NP1) {
+            Eng::template phase<P>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P == NP1 - 1) {
+            if (ok && j == 0) {  // slot 0 of thread 0 is element 0 = sum of x[1..n)
+                cx<T> dc = r.x0 + r.v[0];
+                p.out[g * (uint64_t)p.n] = SWAP ? swap_ri(dc) : dc;
+            }
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                r.v[q] = conj(cmul(r.v[q], ldg(p.mult + e)));
+            }
+            if (j == 0) r.v[0] = r.v[0] + conj(r.x0);
+            Eng::template phase<0>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P >= NP1) {
+            Eng::template phase<P - NP1 + 1>(tid, r.v, smem, p.tw);
+        }
+        if constexpr (P == NPHASE - 1) {
+            cx<T>* dst = p.out + g * (uint64_t)p.n;
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) {
+                const uint32_t e = j + G::TP * q;
+                if (ok) {
+                    cx<T> v = conj(r.v[q]);
+                    dst[ldg_u32(p.ginv + e)] = SWAP ? swap_ri(v) : v;
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Device entry point shared by all kernels.
+// ------------------------------------------------------------------------------------------
+template <class KT, int P>
+struct PhaseRunner {
+    template <class Regs, class S>
+    static B2_HD void run(const typename KT::Params& p, uint32_t bid, int tid, Regs& r, S* smem) {
+        KT::template phase<P>(p, bid, tid, r, smem);
+#if defined(__CUDA_ARCH__)
+        if (P + 1 < KT::NPHASE) __syncthreads();
+#endif
+        if constexpr (P + 1 < KT::NPHASE) PhaseRunner<KT, P + 1>::run(p, bid, tid, r, smem);
+    }
+};
+
+#if defined(__CUDACC__)
+template <class KT>
+__global__ void __launch_bounds__(KT::NT) run_kernel(const __grid_constant__ typename KT::Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename KT::Regs r;
+    PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));
+}
+#endif
+
+}  // namespace b2

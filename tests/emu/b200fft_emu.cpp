@@ -1,0 +1,72 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE, never linked into libb200fft.so.
+//
+// Replays the library's kernel *phase functions* (rustfft_b200/csrc/kernels.h) on the CPU, one
+// CTA at a time, thread by thread, with a barrier between phases -- exactly the structure
+// run_kernel<K> has on the GPU.  It lets the CPU test-suite (no GPU in the build container) check the
+// planner, the twiddle / chirp / index tables and every kernel's index arithmetic through the same
+// C ABI (include/b200fft.h) before GPU time is spent.  "Device" memory is host memory here.
+// What it cannot see: real races, shared-memory limits, launch configuration -- those are what the
+// -m gpu tests are for.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../rustfft_b200/csrc/common.h"
+
+namespace b2 {
+namespace rt {
+typedef void* stream_t;
+static std::string g_err;
+static std::string last_error() { return g_err; }
+static int device_count() { return 1; }
+static bool set_device(int) { return true; }
+static void* dmalloc(size_t n) { return std::malloc(n ? n : 1); }
+static void dfree(void* p) { std::free(p); }
+static bool h2d_sync(void* d, const void* h, size_t n) { std::memcpy(d, h, n); return true; }
+static bool h2d_async(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); return true; }
+static bool d2h_async(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); return true; }
+static bool d2d_async(void* dst, const void* src, size_t n, stream_t) { std::memmove(dst, src, n); return true; }
+static void* malloc_async(size_t n, stream_t) { return std::malloc(n ? n : 1); }
+static void free_async(void* p, stream_t) { std::free(p); }
+static stream_t stream_create() { return (stream_t)1; }
+static void stream_destroy(stream_t) {}
+static bool stream_sync(stream_t) { return true; }
+}  // namespace rt
+}  // namespace b2
+
+#include "../../rustfft_b200/csrc/kernels.h"
+
+namespace b2 {
+namespace rt {
+
+static uint64_t g_launches = 0;
+
+template <class KT, int P>
+struct EmuPhases {
+    static void run(const typename KT::Params& p, uint32_t bid, std::vector<typename KT::Regs>& regs,
+                    cx<typename KT::T>* smem) {
+        for (int tid = 0; tid < KT::NT; ++tid) KT::template phase<P>(p, bid, tid, regs[(size_t)tid], smem);
+        if constexpr (P + 1 < KT::NPHASE) EmuPhases<KT, P + 1>::run(p, bid, regs, smem);
+    }
+};
+
+template <class KT>
+static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t) {
+    ++g_launches;
+    std::vector<typename KT::Regs> regs((size_t)KT::NT);
+    // poison shared memory so a read of a slot nobody wrote shows up as NaN
+    std::vector<cx<typename KT::T>> smem(KT::SMEM_BYTES / sizeof(cx<typename KT::T>) + 1);
+    for (uint64_t bid = 0; bid < ctas; ++bid) {
+        std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
+        EmuPhases<KT, 0>::run(p, (uint32_t)bid, regs, smem.data());
+    }
+    return true;
+}
+
+}  // namespace rt
+}  // namespace b2
+
+#include "../../rustfft_b200/csrc/impl.inl"
+
+extern "C" uint64_t b200fft_emu_launch_count(void) { return b2::rt::g_launches; }
