@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- batched complex-FFT GFLOP/s (5 N log2 N) on B200 vs the HBM roofline.
+
+Workload (BASELINE.json configs[1]): f32 forward, N = 2^10 .. 2^20, batch = 4096 per GPU, synthetic
+U[0,10) complex vectors.  One "step" = one pass of the hot path over that whole sweep (11 sizes).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference ...                          # the reference's CPU path (see below)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...         # one rank per GPU, weak scaling
+
+value   : whole-job GFLOP/s, inputs resident in HBM, CUDA events on the launch stream, max over ranks
+e2e     : same metric through the host-slice C ABI (b200fft_exec_host_outofplace) from pinned host
+          memory -- H2D and D2H inside the timed region (PCIe bound)
+roofline: algorithmic bytes (read + write of the signal = 16 N per f32 transform) /
+          device time, against MEASURED_PEAKS.json hbm_gbs; per size and for the whole step
+cpu_baseline / --impl reference: RustFFT itself cannot be built here (no rustc/cargo in the image), so
+          the reference arm is the C++ restatement of its scalar planner path (oracle/, kind "port")
+          on all host cores, one contiguous batch slice per thread (examples/concurrency.rs), on a
+          bounded sample of the same sweep.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LOGS = list(range(10, 21))
+BATCH = 4096
+METRIC = "batched complex-FFT GFLOP/s (5N log2 N), f32 forward, N=2^10..2^20, batch=4096/GPU"
+
+
+def flops(n: int, batch: int) -> float:
+    return 5.0 * n * math.log2(n) * batch
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_sample(threads: int, reps: int = 8):
+    """Bounded sample of the sweep on the host: per size, 2^24 complex elements (128 MiB), `reps` passes."""
+    import oracle
+
+    total_f, total_t, per = 0.0, 0.0, []
+    for lg in LOGS:
+        n = 1 << lg
+        batch = max(threads, (1 << 24) // n)
+        t = oracle.time_f32(n, batch, threads, reps)
+        f = flops(n, batch) * reps
+        per.append({"log2n": lg, "batch": batch, "gflops": round(f / t / 1e9, 2)})
+        total_f += f
+        total_t += t
+    return total_f / total_t / 1e9, total_t, per
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_sample(cores, reps=1)
+    vals, t_all = [], 0.0
+    for _ in range(args.steps):
+        g, t, per = cpu_sample(cores)
+        vals.append(g)
+        t_all += t
+    value = sum(vals) / len(vals)
+    sample = "per step: every N in 2^10..2^20 with batch = 2^24/N transforms (128 MiB per size), 8 passes each"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_all / args.steps, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "f32 forward N=2^10..2^20 (BASELINE configs[1]); reference arm = C++ port of RustFFT's "
+                               "scalar planner path (RustFFT itself needs rustc, absent from the image)",
+                   "per_size": per},
+        "cpu_baseline": {"value": round(value, 2), "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+
+    import rustfft_b200 as rb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    planner = rb.FftPlanner(np.complex64, device=local_rank)
+    plans = {lg: planner.plan_fft_forward(1 << lg) for lg in LOGS}
+    logs = LOGS if not args.logs else [int(x) for x in args.logs.split(",")]
+
+    # one 32 GiB input region + one 32 GiB output region; sizes below 2^20 live at disjoint offsets so
+    # nothing a size reads was touched since >= 32 GiB of other traffic (no L2 reuse between sizes/steps)
+    max_elems = BATCH << max(logs)
+    offs, o = {}, 0
+    for lg in logs:
+        if lg == max(logs):
+            offs[lg] = 0
+        else:
+            offs[lg] = o
+            o += BATCH << lg
+    src = torch.empty(max_elems, dtype=torch.complex64, device=dev)
+    dst = torch.empty(max_elems, dtype=torch.complex64, device=dev)
+    g = torch.Generator(device=dev).manual_seed(20260922 + rank)
+    step_e = 1 << 26
+    for i in range(0, max_elems, step_e):
+        k = min(step_e, max_elems - i)
+        torch.view_as_real(src[i:i + k]).copy_(torch.rand(k, 2, device=dev, generator=g) * 10)
+    ws_bytes = max(plans[lg].workspace_bytes(BATCH) for lg in logs)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    def one_size(lg):
+        n = 1 << lg
+        a = src[offs[lg]: offs[lg] + BATCH * n]
+        b = dst[offs[lg]: offs[lg] + BATCH * n]
+        plans[lg].process_device(a, out=b, workspace=ws if plans[lg].workspace_bytes(BATCH) else None)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_warm = 1 if args.profile else max(args.warmup, 3)
+    for _ in range(n_warm):
+        for lg in logs:
+            one_size(lg)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(logs) + 1)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for i, lg in enumerate(logs):
+            one_size(lg)
+            ev[s][i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0][0].elapsed_time(ev[-1][-1])
+    per_ms = {lg: sum(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) / args.steps
+              for i, lg in enumerate(logs)}
+    if dist:
+        t = torch.tensor([total_ms] + [per_ms[lg] for lg in logs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = t[0].item()
+        per_ms = {lg: t[i + 1].item() for i, lg in enumerate(logs)}
+
+    hbm, peak_src = peaks()
+    step_ms = total_ms / args.steps
+    step_flops = sum(flops(1 << lg, BATCH) for lg in logs)
+    step_bytes = sum(16.0 * (1 << lg) * BATCH for lg in logs)
+    value = step_flops * world / (step_ms * 1e-3) / 1e9
+    per_size = []
+    for lg in logs:
+        gbs = 16.0 * (1 << lg) * BATCH / (per_ms[lg] * 1e-3) / 1e9
+        per_size.append({"log2n": lg, "plan": plans[lg].describe(), "ms": round(per_ms[lg], 4),
+                         "gflops": round(flops(1 << lg, BATCH) / (per_ms[lg] * 1e-3) / 1e9, 1),
+                         "gbs": round(gbs, 1), "frac": round(gbs / hbm, 4)})
+    achieved = step_bytes / (step_ms * 1e-3) / 1e9
+    launches = sum(plans[lg].launches(BATCH) for lg in logs) * args.steps
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+
+    # ---- e2e: the host-slice trait path from pinned host memory (rank-local), PCIe inside the timing
+    e2e = None
+    if not args.no_e2e:
+        cap = int(args.e2e_pinned_gib * (1 << 30)) // 8
+        hin = torch.empty(min(cap, max_elems), dtype=torch.complex64).pin_memory()
+        hout = torch.empty_like(hin).pin_memory()
+        torch.view_as_real(hin).uniform_(0, 10)
+        hin_np, hout_np = hin.numpy(), hout.numpy()
+
+        def e2e_step():
+            for lg in logs:
+                n = 1 << lg
+                todo = BATCH
+                per_call = max(1, min(BATCH, hin_np.size // n))
+                while todo:
+                    nb = min(per_call, todo)
+                    plans[lg].process_outofplace_with_scratch(hin_np[: nb * n], hout_np[: nb * n])
+                    todo -= nb
+
+        e2e_step()  # warm-up (staging allocations, page faults)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        if dist:
+            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = tt.item()
+        e2e = {"value": round(step_flops * world / e2e_s / 1e9, 1), "unit": "GFLOP/s",
+               "h2d_bytes_per_step": int(step_bytes // 2) * world, "d2h_bytes_per_step": int(step_bytes // 2) * world,
+               "ms_per_step": round(e2e_s * 1e3, 1), "steps": args.e2e_steps,
+               "how": "b200fft_exec_host_outofplace on pinned host buffers (wall clock incl. H2D+D2H), "
+                      f"{args.e2e_pinned_gib} GiB pinned window reused per call"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+
+        oracle.build()
+        cores = os.cpu_count() or 1
+        cpu_sample(cores, reps=1)
+        gcpu, tcpu, _ = cpu_sample(cores, reps=4)
+        cpu = {"value": round(gcpu, 2), "unit": "GFLOP/s", "cores": cores, "kind": "port",
+               "sample": "every N in 2^10..2^20, batch = 2^24/N transforms per size, 4 passes "
+                         f"({tcpu:.1f} s of CPU work); C++ port of RustFFT's scalar planner path, one batch slice per thread"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(value, 1), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": n_warm, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: f32 forward, N=2^10..2^20, batch=4096 per GPU, out of place, "
+                                   "device resident", "sizes_log2": logs, "batch_per_gpu": BATCH,
+                       "l2_policy": "inputs larger than L2: each size has its own region of a 32 GiB buffer, "
+                                    ">= 32 GiB of other traffic between two touches of any byte",
+                       "per_size": per_size},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                         "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "whole step (every launch in it is one of this repo's FFT passes); "
+                                   "dominant = FourStep{1024x1024} passes A+B at N=2^20",
+                         "algorithmic_bytes_per_step": int(step_bytes)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--logs", default="", help="comma list of log2 sizes (debug); default 10..20")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-pinned-gib", type=float, default=4.0)
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / cpu legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.profile:
+        args.no_e2e = args.no_cpu = True
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

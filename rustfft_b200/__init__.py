@@ -245,7 +245,7 @@ class Fft:
         n = x.numel()
         if self._len == 0 or n == 0:
             return dst
-        if n < self._len:
+        if n < self._len:  # (an empty buffer is zero chunks and validates, src/array_utils.rs:151-177)
             raise FftError(-4, f"Provided FFT buffer was too small. Expected len = {self._len}, got len = {n}")
         if n % self._len:
             raise FftError(-5, "Input FFT buffer must be a multiple of FFT length. "

@@ -456,6 +456,7 @@ static int validate_len(const b200fft_plan* pl, uint64_t n_in, uint64_t n_out, b
         return fail(B200FFT_ERR_LEN_MISMATCH,
                     "Provided FFT input buffer and output buffer must have the same length. Got input.len() = " +
                         std::to_string(n_in) + ", output.len() = " + std::to_string(n_out));
+    if (n_in == 0) return B200FFT_OK;  // zero chunks validate fine (src/array_utils.rs:151-177)
     if (n_in < len)
         return fail(B200FFT_ERR_BUFFER_TOO_SMALL, "Provided FFT buffer was too small. Expected len = " +
                                                       std::to_string(len) + ", got len = " + std::to_string(n_in));

@@ -1,0 +1,94 @@
+"""CPU (`-m "not gpu"`): the library's planner, tables and kernel phase functions, replayed on the
+CPU by tests/emu behind the real C ABI, checked with the reference's protocol against the oracle.
+This is host-logic coverage; the parity tests proper are tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import oracle
+import rustfft_b200 as rb
+from protocol import check_error_behaviour, check_fft_algorithm, check_planner_cache
+from util import emu_library, rel_l2, signal, truth
+
+DIRS = [rb.FftDirection.Forward, rb.FftDirection.Inverse]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_library()
+
+
+@pytest.fixture(scope="module", params=[np.complex64, np.complex128], ids=["f32", "f64"])
+def planner(request, lib):
+    return rb.FftPlanner(request.param, lib=lib), request.param
+
+
+def test_every_len_1_to_200_both_directions(planner):
+    pl, dtype = planner
+    for n in range(1, 201):
+        for d in DIRS:
+            check_fft_algorithm(pl, n, d, dtype)
+
+
+def test_sampled_lens_up_to_1000_and_plan_kinds(planner):
+    pl, dtype = planner
+    seen = set()
+    for n in list(range(201, 1001, 37)) + [255, 256, 257, 511, 512, 617, 719, 991, 997, 1000, 1024, 1234, 2047, 2048]:
+        f = check_fft_algorithm(pl, n, DIRS[n % 2], dtype)
+        seen.add(f.describe().split("{")[0])
+    assert {"Direct", "Bluestein", "Rader"} <= seen
+
+
+@pytest.mark.parametrize("n,desc", [(2048, "Direct{2048}"), (4096, "Direct{4096}"), (8192, "FourStep{64x128}"),
+                                    (1 << 14, "FourStep{128x128}"), (1 << 15, "FourStep{128x256}"),
+                                    (1 << 16, "FourStep{256x256}"), (1 << 17, "FourStep{256x512}")])
+def test_power_of_two_plans(planner, n, desc):
+    pl, dtype = planner
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
+    assert f.describe() == desc
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
+
+
+def test_largest_four_step_f32(lib):
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    f = check_fft_algorithm(pl, 1 << 20, DIRS[0], np.complex64, control_kind=oracle.PLANNER, chunks=1)
+    assert f.describe() == "FourStep{1024x1024}"
+
+
+def test_chunked_four_step_matches_unchunked(lib, monkeypatch):
+    # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    n, batch = 1 << 16, 70
+    x = signal(n * batch, np.complex64, seed=5)
+    f = pl.plan_fft_forward(n)
+    assert f.launches(batch) == 4 and f.workspace_bytes(batch) == 64 * n * 8
+    y = x.copy()
+    f.process(y)
+    for b in (0, 63, 64, 69):
+        assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * 16
+
+
+def test_error_behaviour_and_cache(planner):
+    pl, dtype = planner
+    check_error_behaviour(pl, dtype)
+    check_planner_cache(pl)
+
+
+def test_unsupported_lengths_fail_loudly(lib):
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    with pytest.raises(rb.FftError, match="not planned by this build"):
+        pl.plan_fft_forward(1 << 21)
+
+
+def test_linearity_roundtrip_parseval(planner):
+    pl, dtype = planner
+    n = 1234
+    a, b = signal(n, dtype, 1), signal(n, dtype, 2)
+    f, fi = pl.plan_fft_forward(n), pl.plan_fft_inverse(n)
+    fa, fb, fab = a.copy(), b.copy(), (a + 2 * b).astype(dtype)
+    f.process(fa), f.process(fb), f.process(fab)
+    tol = 64 * (5.96e-8 if dtype == np.complex64 else 1.11e-16)
+    assert rel_l2(fab, fa + 2 * fb) < tol
+    back = fa.copy()
+    fi.process(back)
+    assert rel_l2(back / n, a) < tol  # unnormalised both ways (src/lib.rs:81-85)
+    assert abs(np.sum(np.abs(fa.astype(np.complex128)) ** 2) / n / np.sum(np.abs(a.astype(np.complex128)) ** 2) - 1) < tol

@@ -1,0 +1,192 @@
+"""GPU (`-m gpu`): the parity tests proper.  The hand-written sm_100a kernels, called through the
+C ABI (include/b200fft.h) via the FftPlanner / Fft mirror, against the CPU oracle on the same seeded
+inputs -- the reference's acceptance test (tests/accuracy.rs:124-187: every len 1..1000, forward and
+inverse, f32 and f64, three process variants, vs the Bluestein-over-Radix4 control) plus the
+BASELINE.json configs, with the reference's criterion (mean |a-b| < 0.1) AND the strict tolerance
+stated in tests/util.py::strict_bound (relative L2 <= 4 eps log2 N vs an f64 truth, and never worse
+than 2x the oracle's own error).  Full-size configs are checked through size-independent properties
+(round trip, Parseval, linearity) with spot transforms compared to the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle
+import rustfft_b200 as rb
+from protocol import check_error_behaviour, check_fft_algorithm, check_planner_cache
+from util import EPS, rel_l2, signal, strict_bound, truth
+
+pytestmark = pytest.mark.gpu
+DIRS = [rb.FftDirection.Forward, rb.FftDirection.Inverse]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    return torch
+
+
+@pytest.fixture(scope="module", params=[np.complex64, np.complex128], ids=["f32", "f64"])
+def planner(request, torch_cuda):
+    # default library = rustfft_b200/libb200fft.so; raises if it is missing (no fallback)
+    return rb.FftPlanner(request.param, device=0), request.param
+
+
+def test_native_library_is_the_one_running(torch_cuda):
+    lib = rb.default_library()
+    assert lib.path.endswith("rustfft_b200/libb200fft.so") and lib.device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libb200fft.so" in maps and "libb200fft_emu" not in maps
+
+
+def test_accuracy_every_len_1_to_1000(planner):
+    """tests/accuracy.rs:124-187."""
+    pl, dtype = planner
+    for n in range(1, 1001):
+        for d in DIRS:
+            check_fft_algorithm(pl, n, d, dtype)
+
+
+@pytest.mark.parametrize("lg", list(range(10, 21)))
+def test_config2_power_of_two_sweep_vs_oracle(torch_cuda, lg):
+    """BASELINE config 2 (f32 forward 2^10..2^20): a few transforms against the scalar-planner oracle
+    (Radix4, src/algorithm/radix4.rs) and the f64 truth."""
+    pl = rb.FftPlanner(np.complex64)
+    n = 1 << lg
+    check_fft_algorithm(pl, n, DIRS[0], np.complex64, control_kind=oracle.PLANNER, chunks=3 if lg < 18 else 1)
+    check_fft_algorithm(pl, n, DIRS[1], np.complex64, control_kind=oracle.PLANNER, chunks=1)
+
+
+@pytest.mark.parametrize("lg", [10, 13, 16, 18, 20])
+def test_config2_full_batch_properties(torch_cuda, lg):
+    """batch = 4096 on the device path: inverse(forward(x))/N == x, Parseval, linearity in the batch,
+    and first / last / middle transforms against the oracle."""
+    torch = torch_cuda
+    n, batch = 1 << lg, 4096
+    pl = rb.FftPlanner(np.complex64)
+    f, fi = pl.plan_fft_forward(n), pl.plan_fft_inverse(n)
+    g = torch.Generator(device="cuda").manual_seed(lg)
+    x = torch.rand(batch * n, 2, device="cuda", generator=g) * 10
+    x = torch.view_as_complex(x).contiguous()
+    y = torch.empty_like(x)
+    f.process_device(x, out=y)
+    ex = torch.sum(x.real.double() ** 2 + x.imag.double() ** 2)
+    ey = torch.sum(y.real.double() ** 2 + y.imag.double() ** 2) / n
+    assert abs((ey / ex).item() - 1) < 1e-5  # Parseval
+    for b in (0, batch // 2 + 1, batch - 1):
+        xb = x[b * n:(b + 1) * n].cpu().numpy()
+        yb = y[b * n:(b + 1) * n].cpu().numpy()
+        assert rel_l2(yb, truth(xb, n, False)) <= strict_bound(n, np.complex64)
+        assert rel_l2(yb, oracle.fft(xb, n)) <= 2 * strict_bound(n, np.complex64)
+    fi.process_device(y)  # in place
+    y /= n
+    num = torch.sqrt(torch.sum((y.real - x.real).double() ** 2 + (y.imag - x.imag).double() ** 2))
+    assert (num / torch.sqrt(ex)).item() <= 2 * strict_bound(n, np.complex64)
+    del y
+    torch.cuda.empty_cache()
+
+
+def test_config3_f64_1234_roundtrip_batch_1024(torch_cuda):
+    """BASELINE config 3: f64 forward + inverse round trip, N = 1234, batch = 1024."""
+    n, batch = 1234, 1024
+    pl = rb.FftPlanner(np.complex128)
+    f, fi = pl.plan_fft_forward(n), pl.plan_fft_inverse(n)
+    x = signal(n * batch, np.complex128, seed=3)
+    y = x.copy()
+    f.process(y)
+    for b in (0, 511, 1023):
+        got, xb = y[b * n:(b + 1) * n], x[b * n:(b + 1) * n]
+        want = oracle.fft(xb, n)  # RadixN{[2], Raders(617)} in the scalar planner
+        assert rel_l2(got, truth(xb, n, False)) <= max(strict_bound(n, np.complex128), 2 * rel_l2(want, truth(xb, n, False)))
+    fi.process(y)
+    assert rel_l2(y / n, x) <= 2 * strict_bound(n, np.complex128)
+
+
+def test_config4_prime_65537_batch_512(torch_cuda):
+    """BASELINE config 4: f32 prime N = 65537 (Rader in both reference planners), batch = 512."""
+    n, batch = 65537, 512
+    pl = rb.FftPlanner(np.complex64)
+    try:
+        f = pl.plan_fft_forward(n)
+    except rb.FftError as e:
+        pytest.xfail(f"65537 not planned yet: {e}")
+    x = signal(n * batch, np.complex64, seed=4)
+    y = x.copy()
+    f.process(y)
+    for b in (0, 255, 511):
+        xb = x[b * n:(b + 1) * n]
+        ref = truth(xb, n, False)
+        want = oracle.fft(xb, n)
+        assert rel_l2(y[b * n:(b + 1) * n], ref) <= max(strict_bound(n, np.complex64), 2 * rel_l2(want, ref))
+
+
+def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
+    torch = torch_cuda
+    pl = rb.FftPlanner(np.complex64)
+    for n, batch in [(1024, 33), (1 << 15, 70), (1 << 16, 5), (257, 9), (1000, 17)]:
+        f = pl.plan_fft_forward(n)
+        x = signal(n * batch, np.complex64, seed=n)
+        host = x.copy()
+        f.process(host)
+        d = torch.from_numpy(x).cuda()
+        out = torch.full_like(d, float("nan"))
+        f.process_device(d, out=out)
+        assert np.array_equal(out.cpu().numpy(), host), n
+        assert np.array_equal(d.cpu().numpy(), x), "out-of-place must leave the input intact"
+        f.process_device(d)  # in place
+        assert np.array_equal(d.cpu().numpy(), host), n
+        nbytes = f.workspace_bytes(batch)
+        if nbytes:
+            ws = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device="cuda")  # dirty workspace
+            d2 = torch.from_numpy(x).cuda()
+            f.process_device(d2, workspace=ws)
+            assert np.array_equal(d2.cpu().numpy(), host), n
+            with pytest.raises(rb.FftError, match="workspace too small"):
+                f.process_device(d2, workspace=ws[: nbytes // 2])
+
+
+def test_error_behaviour_and_cache(planner):
+    pl, dtype = planner
+    check_error_behaviour(pl, dtype)
+    check_planner_cache(pl)
+
+
+def test_shared_plan_from_many_threads(torch_cuda):
+    """examples/concurrency.rs:17-29: one Arc<dyn Fft> used by several threads at once."""
+    torch = torch_cuda
+    pl = rb.FftPlanner(np.complex64)
+    f = pl.plan_fft_forward(1 << 14)  # FourStep: needs a per-call workspace
+    n = 1 << 14
+    xs = [signal(n * 8, np.complex64, seed=t) for t in range(6)]
+    outs = [None] * 6
+
+    def work(t):
+        with torch.cuda.stream(torch.cuda.Stream()):
+            d = torch.from_numpy(xs[t]).cuda()
+            for _ in range(5):
+                o = torch.empty_like(d)
+                f.process_device(d, out=o)
+            torch.cuda.current_stream().synchronize()
+            outs[t] = o.cpu().numpy()
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for t in range(6):
+        want = xs[t].copy()
+        f.process(want)
+        assert np.array_equal(outs[t], want), t
+
+
+def test_ragged_batches_and_tails(torch_cuda):
+    """batch sizes that do not fill the last CTA (F transforms per CTA) or the last L2 chunk."""
+    pl = rb.FftPlanner(np.complex64)
+    for n, batches in [(8, [1, 127, 129]), (64, [1, 15, 17]), (256, [1, 7, 9]), (1 << 13, [1, 3]), (100, [1, 15, 17])]:
+        f = pl.plan_fft_forward(n)
+        for b in batches:
+            x = signal(n * b, np.complex64, seed=b)
+            y = x.copy()
+            f.process(y)
+            assert rel_l2(y, truth(x, n, False)) <= strict_bound(n, np.complex64), (n, b)
