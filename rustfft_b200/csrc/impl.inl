@@ -295,6 +295,152 @@ struct Builder {
         return true;
     }
 
+    // ---------------- large convolution plans (Rader / Bluestein over a four-step inner FFT) -------
+    //   A1: gather|chirp-pad columns -> N1-pt FFT -> twiddle            in   -> w1
+    //   B1: rows -> N2-pt FFT -> * mult, conj (+ Rader DC)               w1   -> w2 (natural order)
+    //   A2: columns -> N1-pt FFT -> twiddle (plain pass A, in place)     w2   -> w2
+    //   B2: rows -> N2-pt FFT -> conj + scatter | conj * chirp           w2   -> out
+    struct ConvTables {
+        const uint32_t* gather = nullptr;   // Rader: g^(i+1) mod n
+        const uint32_t* scatter = nullptr;  // Rader: g^-(i+1) mod n
+        const C* chirp = nullptr;           // Bluestein: W_2n^(i^2)
+        const C* mult = nullptr;            // M entries
+        uint32_t n = 0, lgM = 0, lg1 = 0, lg2 = 0;
+        bool rader = false;
+    };
+    struct ConvFns {
+        std::function<bool(const C* in, C* w1, uint64_t nb, rt::stream_t)> a1;
+        std::function<bool(const C* w1, C* w2, const C* in, C* out, uint64_t nb, rt::stream_t)> b1;
+        std::function<bool(const C* w2, C* out, uint64_t nb, rt::stream_t)> b2;
+    };
+    template <int L1, bool SW>
+    static bool make_conv_a1(b200fft_plan& pl, const ConvTables& t, TwoLevelTw<T> tl, ConvFns& f) {
+        using G = typename TileGeo<T, L1>::type;
+        using KT = FftKernel<G, FF, FF, LoadColsConv<T, SW>, StoreColsTw<T>>;
+        const C* tw = upload(pl, stage_twiddles<G>());
+        if (!tw) return false;
+        f.a1 = [=](const C* in, C* w1, uint64_t nb, rt::stream_t s) {
+            typename KT::Params p;
+            p.load = LoadColsConv<T, SW>{in, t.gather, t.chirp, t.n, t.lg2};
+            p.store = StoreColsTw<T>{w1, t.lgM, t.lg2, tl};
+            p.tw = tw;
+            p.n_fft = nb << t.lg2;
+            return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
+        };
+        return true;
+    }
+    template <int L2, bool SW>
+    static bool make_conv_b(b200fft_plan& pl, const ConvTables& t, ConvFns& f) {
+        using G = typename TileGeo<T, L2>::type;
+        using K0 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 0>>;
+        const C* tw = upload(pl, stage_twiddles<G>());
+        if (!tw) return false;
+        f.b1 = [=](const C* w1, C* w2, const C* in, C* out, uint64_t nb, rt::stream_t s) {
+            typename K0::Params p;
+            p.load = LoadRows<T, false>{w1, (uint32_t)L2};
+            p.store = StoreTransposedConv<T, SW, 0>{w2, t.mult, nullptr, nullptr, t.rader ? in : nullptr, out, t.n, t.lgM, t.lg1};
+            p.tw = tw;
+            p.n_fft = nb << t.lg1;
+            return rt::launch<K0>(p, (p.n_fft + G::F - 1) / G::F, s);
+        };
+        if (t.rader) {
+            using K1 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 1>>;
+            f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
+                typename K1::Params p;
+                p.load = LoadRows<T, false>{w2, (uint32_t)L2};
+                p.store = StoreTransposedConv<T, SW, 1>{out, nullptr, t.scatter, nullptr, nullptr, nullptr, t.n, t.lgM, t.lg1};
+                p.tw = tw;
+                p.n_fft = nb << t.lg1;
+                return rt::launch<K1>(p, (p.n_fft + G::F - 1) / G::F, s);
+            };
+        } else {
+            using K2 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 2>>;
+            f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
+                typename K2::Params p;
+                p.load = LoadRows<T, false>{w2, (uint32_t)L2};
+                p.store = StoreTransposedConv<T, SW, 2>{out, nullptr, nullptr, t.chirp, nullptr, nullptr, t.n, t.lgM, t.lg1};
+                p.tw = tw;
+                p.n_fft = nb << t.lg1;
+                return rt::launch<K2>(p, (p.n_fft + G::F - 1) / G::F, s);
+            };
+        }
+        return true;
+    }
+    template <bool SW>
+    static bool make_conv_rt(b200fft_plan& pl, const ConvTables& t, TwoLevelTw<T> tl, ConvFns& f, PassFns& plain) {
+        bool ok = false;
+        switch (1u << t.lg1) {
+            case 64: ok = make_conv_a1<64, SW>(pl, t, tl, f) && make_pass_a<64, false>(pl, t.lgM, t.lg2, tl, plain); break;
+            case 128: ok = make_conv_a1<128, SW>(pl, t, tl, f) && make_pass_a<128, false>(pl, t.lgM, t.lg2, tl, plain); break;
+            case 256: ok = make_conv_a1<256, SW>(pl, t, tl, f) && make_pass_a<256, false>(pl, t.lgM, t.lg2, tl, plain); break;
+            case 512: ok = make_conv_a1<512, SW>(pl, t, tl, f) && make_pass_a<512, false>(pl, t.lgM, t.lg2, tl, plain); break;
+            case 1024: ok = make_conv_a1<1024, SW>(pl, t, tl, f) && make_pass_a<1024, false>(pl, t.lgM, t.lg2, tl, plain); break;
+        }
+        if (!ok) return false;
+        switch (1u << t.lg2) {
+            case 64: return make_conv_b<64, SW>(pl, t, f);
+            case 128: return make_conv_b<128, SW>(pl, t, f);
+            case 256: return make_conv_b<256, SW>(pl, t, f);
+            case 512: return make_conv_b<512, SW>(pl, t, f);
+            case 1024: return make_conv_b<1024, SW>(pl, t, f);
+        }
+        return false;
+    }
+    // rader = true: n prime, M = n - 1;  rader = false: Bluestein, M = next_pow2(2n - 1)
+    static bool make_big_conv(b200fft_plan& pl, uint64_t M, bool rader) {
+        const uint64_t n = pl.len;
+        ConvTables t;
+        t.n = (uint32_t)n;
+        t.lgM = hm::ilog2(M);
+        t.lg1 = t.lgM / 2;
+        t.lg2 = t.lgM - t.lg1;
+        t.rader = rader;
+        if ((1u << t.lg1) < TILE_MIN || (1u << t.lg2) > TILE_MAX) return false;
+        std::vector<C> mult;
+        uint64_t groot = 0;
+        if (rader) {
+            std::vector<uint32_t> gpow, ginv;
+            rader_tables(n, M, gpow, ginv, mult, groot);
+            t.gather = upload(pl, gpow);
+            t.scatter = upload(pl, ginv);
+            if (!t.gather || !t.scatter) return false;
+        } else {
+            std::vector<C> chirp;
+            bluestein_tables(n, M, chirp, mult);
+            t.chirp = upload(pl, chirp);
+            if (!t.chirp) return false;
+        }
+        t.mult = upload(pl, mult);
+        if (!t.mult) return false;
+        TwoLevelTw<T> tl;
+        if (!make_two_level(pl, t.lgM, tl)) return false;
+        ConvFns f;
+        PassFns plain;
+        const bool ok = pl.direction ? make_conv_rt<true>(pl, t, tl, f, plain) : make_conv_rt<false>(pl, t, tl, f, plain);
+        if (!ok) return false;
+        const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / 2 / (M * sizeof(C)));
+        pl.work_bytes = [=](uint64_t batch) { return 2 * std::min(batch, chunk) * M * sizeof(C); };
+        pl.launches = [=](uint64_t batch) { return 4 * ((batch + chunk - 1) / chunk); };
+        pl.exec = [=](const ExecCtx& c) {
+            const C* in = (const C*)c.in;
+            C* out = (C*)c.out;
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                C* w1 = (C*)c.work;
+                C* w2 = w1 + std::min(c.batch, chunk) * M;
+                if (!f.a1(in + b0 * n, w1, nb, c.stream)) return false;
+                if (!f.b1(w1, w2, in + b0 * n, out + b0 * n, nb, c.stream)) return false;
+                if (!plain.a(w2, w2, nb, c.stream)) return false;
+                if (!f.b2(w2, out + b0 * n, nb, c.stream)) return false;
+            }
+            return true;
+        };
+        const std::string inner = "FourStep{" + std::to_string(1u << t.lg1) + "x" + std::to_string(1u << t.lg2) + "}";
+        pl.desc = rader ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + "}"
+                        : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + "}";
+        return true;
+    }
+
     // ---------------- Bluestein (fused) ----------------
     static void bluestein_tables(uint64_t n, uint64_t M, std::vector<C>& chirp, std::vector<C>& mult) {
         chirp.resize((size_t)n);
@@ -358,28 +504,36 @@ struct Builder {
     }
 
     // ---------------- Rader (fused) ----------------
+    // gpow[i] = g^(i+1) mod n, ginv[i] = g^-(i+1) mod n, mult = FFT_M( twiddle(g^-i mod n, n) / M )
+    static void rader_tables(uint64_t n, uint64_t M, std::vector<uint32_t>& gpow, std::vector<uint32_t>& ginv,
+                             std::vector<C>& mult, uint64_t& g) {
+        g = hm::primitive_root(n);
+        const uint64_t gi = hm::powmod(g, n - 2, n);
+        gpow.resize((size_t)M);
+        ginv.resize((size_t)M);
+        std::vector<hm::cld> d((size_t)M);
+        uint64_t a = 1, b = 1;
+        for (uint64_t i = 0; i < M; ++i) {
+            const hm::cld w = hm::twiddle_ld(b, n);  // b = g^-i
+            d[(size_t)i] = hm::cld{w.x / (hm::ld)M, w.y / (hm::ld)M};
+            a = hm::mulmod(a, g, n);
+            b = hm::mulmod(b, gi, n);
+            gpow[(size_t)i] = (uint32_t)a;
+            ginv[(size_t)i] = (uint32_t)b;
+        }
+        hm::fft_pow2_ld(d);
+        mult.resize((size_t)M);
+        for (size_t i = 0; i < (size_t)M; ++i) mult[i] = mk<T>((T)d[i].x, (T)d[i].y);
+    }
     template <int M, bool SW>
     static bool make_rader_t(b200fft_plan& pl) {
         using G = typename DirectGeo<T, M>::type;
         using KT = RaderKernel<G, SW>;
         const uint64_t n = pl.len;
-        const uint64_t g = hm::primitive_root(n);
-        const uint64_t gi = hm::powmod(g, n - 2, n);
-        std::vector<uint32_t> gpow((size_t)M), ginv((size_t)M);
-        std::vector<hm::cld> d((size_t)M);
-        uint64_t a = 1, b = 1;
-        for (uint64_t i = 0; i < (uint64_t)M; ++i) {
-            // d[i] = twiddle(g^-i mod n, n) / M   (b = g^-i before the update)
-            const hm::cld w = hm::twiddle_ld(b, n);
-            d[(size_t)i] = hm::cld{w.x / (hm::ld)M, w.y / (hm::ld)M};
-            a = hm::mulmod(a, g, n);
-            b = hm::mulmod(b, gi, n);
-            gpow[(size_t)i] = (uint32_t)a;  // g^(i+1)
-            ginv[(size_t)i] = (uint32_t)b;  // g^-(i+1)
-        }
-        hm::fft_pow2_ld(d);
-        std::vector<C> mult((size_t)M);
-        for (size_t i = 0; i < (size_t)M; ++i) mult[i] = mk<T>((T)d[i].x, (T)d[i].y);
+        std::vector<uint32_t> gpow, ginv;
+        std::vector<C> mult;
+        uint64_t g = 0;
+        rader_tables(n, (uint64_t)M, gpow, ginv, mult, g);
         const uint32_t* d_gpow = upload(pl, gpow);
         const uint32_t* d_ginv = upload(pl, ginv);
         const C* d_mult = upload(pl, mult);
@@ -436,13 +590,17 @@ struct Builder {
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^20 are not planned by this build");
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
+        } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {
+            ok = make_big_conv(pl, n - 1, true);  // 65537
         } else {
             const uint64_t M = hm::next_pow2(2 * n - 1);
             if (M <= DIRECT_MAX)
                 ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
+            else if (M <= (uint64_t)TILE_MAX * TILE_MAX)
+                ok = make_big_conv(pl, M, false);
             else
                 return fail(B200FFT_ERR_UNSUPPORTED,
-                            "non-power-of-two lengths above " + std::to_string(DIRECT_MAX / 2) + " are not planned by this build");
+                            "non-power-of-two lengths above 2^19 are not planned by this build");
         }
         if (!ok) return fail(B200FFT_ERR_CUDA, "plan construction failed: " + rt::last_error());
         return B200FFT_OK;

@@ -120,6 +120,90 @@ struct StoreTransposed {
 };
 
 // ------------------------------------------------------------------------------------------
+// Functors of the large convolution plans (Rader / Bluestein with an inner FFT of M = N1*N2 > one
+// CTA): the same two four-step passes, with the algorithm's gather / chirp / pointwise / scatter
+// steps folded into the first pass' loads and the second pass' stores, so no step of
+// src/algorithm/raders_algorithm.rs:235-283 / bluesteins_algorithm.rs:100-136 is a separate sweep
+// over memory.
+// ------------------------------------------------------------------------------------------
+// pass A load of the FIRST inner FFT.  Inner element i = e*N2 + c of transform b comes from
+//   gather != null (Rader):     in[b*n + gather[i]]            gather[i] = g^(i+1) mod n
+//   gather == null (Bluestein): i < n ? in[b*n + i] * chirp[i] : 0
+template <typename T, bool SWAP>
+struct LoadColsConv {
+    const cx<T>* in;
+    const uint32_t* gather;
+    const cx<T>* chirp;
+    uint32_t n;    // outer length = stride between transforms of `in`
+    uint32_t lg2;  // log2 N2 (inner)
+    struct St { const cx<T>* p; uint32_t c; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg2;
+        return St{in + b * (uint64_t)n, (uint32_t)(g & ((1ull << lg2) - 1)), ok};
+    }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        const uint32_t i = ((uint32_t)e << lg2) + s.c;
+        if (gather) {
+            cx<T> v = s.p[ldg_u32(gather + i)];
+            return SWAP ? swap_ri(v) : v;
+        }
+        if (i >= n) return mk<T>(0, 0);
+        cx<T> v = ld_stream(s.p + i);
+        if (SWAP) v = swap_ri(v);
+        return cmul(v, ldg(chirp + i));
+    }
+};
+
+// pass B store of the inner FFTs.  FFT g = (transform b, row k1); output e lands on inner index
+// k = k1 + N1*e.
+//   MODE 0 (end of inner FFT #1): work[b*M + k] = conj(v * mult[k]); Rader (x_in != null) also does
+//           the DC bookkeeping at k == 0:  out[b*n] = x0 + v,  and adds conj(x0) to the stored value
+//   MODE 1 (end of inner FFT #2, Rader):     out[b*n + scatter[k]] = conj(v)    scatter[k] = g^-(k+1) mod n
+//   MODE 2 (end of inner FFT #2, Bluestein): k < n: out[b*n + k] = conj(v) * chirp[k]
+template <typename T, bool SWAP, int MODE>
+struct StoreTransposedConv {
+    cx<T>* out;            // MODE 0: work (stride M); MODE 1/2: user output (stride n)
+    const cx<T>* mult;     // MODE 0
+    const uint32_t* scatter;  // MODE 1
+    const cx<T>* chirp;    // MODE 2
+    const cx<T>* x_in;     // MODE 0, Rader: user input (stride n), else null
+    cx<T>* x_out;          // MODE 0, Rader: user output (stride n)
+    uint32_t n;            // outer length
+    uint32_t lgM, lg1;
+    struct St { cx<T>* p; uint64_t b; uint32_t k1; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg1;
+        const uint32_t k1 = (uint32_t)(g & ((1ull << lg1) - 1));
+        cx<T>* p = (MODE == 0) ? out + (b << lgM) : out + b * (uint64_t)n;
+        return St{p, b, k1, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (!s.ok) return;
+        const uint32_t k = s.k1 + ((uint32_t)e << lg1);
+        if (MODE == 0) {
+            cx<T> w = conj(cmul(v, ldg(mult + k)));
+            if (x_in != nullptr && k == 0) {
+                cx<T> x0 = x_in[s.b * (uint64_t)n];
+                if (SWAP) x0 = swap_ri(x0);
+                const cx<T> dc = x0 + v;
+                x_out[s.b * (uint64_t)n] = SWAP ? swap_ri(dc) : dc;
+                w = w + conj(x0);
+            }
+            s.p[k] = w;
+        } else if (MODE == 1) {
+            const cx<T> w = conj(v);
+            s.p[ldg_u32(scatter + k)] = SWAP ? swap_ri(w) : w;
+        } else {
+            if (k < n) {
+                const cx<T> w = cmul(conj(v), ldg(chirp + k));
+                st_stream(s.p + k, SWAP ? swap_ri(w) : w);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 template <class G, Map M0, Map M1, class Load, class Store>
 struct FftKernel {
     using T = typename G::T;

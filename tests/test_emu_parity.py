@@ -54,6 +54,19 @@ def test_largest_four_step_f32(lib):
     assert f.describe() == "FourStep{1024x1024}"
 
 
+@pytest.mark.parametrize("n,desc", [
+    (65537, "Rader{n=65537,g=3,inner=FourStep{256x256}}"),          # BASELINE config 4
+    (2049, "Bluestein{n=2049,M=8192,inner=FourStep{64x128}}"),
+    (10007, "Bluestein{n=10007,M=32768,inner=FourStep{128x256}}"),
+    (112501, "Bluestein{n=112501,M=262144,inner=FourStep{512x512}}"),  # a 32-bit-overflow prime of raders_algorithm.rs:311-322
+])
+def test_large_convolution_plans(planner, n, desc):
+    pl, dtype = planner
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
+    assert f.describe() == desc
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
+
+
 def test_chunked_four_step_matches_unchunked(lib, monkeypatch):
     # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk
     pl = rb.FftPlanner(np.complex64, lib=lib)
@@ -77,6 +90,8 @@ def test_unsupported_lengths_fail_loudly(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     with pytest.raises(rb.FftError, match="not planned by this build"):
         pl.plan_fft_forward(1 << 21)
+    with pytest.raises(rb.FftError, match="not planned by this build"):
+        pl.plan_fft_forward((1 << 19) + 1)
 
 
 def test_linearity_roundtrip_parseval(planner):

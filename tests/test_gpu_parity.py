@@ -108,10 +108,8 @@ def test_config4_prime_65537_batch_512(torch_cuda):
     """BASELINE config 4: f32 prime N = 65537 (Rader in both reference planners), batch = 512."""
     n, batch = 65537, 512
     pl = rb.FftPlanner(np.complex64)
-    try:
-        f = pl.plan_fft_forward(n)
-    except rb.FftError as e:
-        pytest.xfail(f"65537 not planned yet: {e}")
+    f = pl.plan_fft_forward(n)
+    assert f.describe().startswith("Rader{n=65537")
     x = signal(n * batch, np.complex64, seed=4)
     y = x.copy()
     f.process(y)
@@ -122,10 +120,19 @@ def test_config4_prime_65537_batch_512(torch_cuda):
         assert rel_l2(y[b * n:(b + 1) * n], ref) <= max(strict_bound(n, np.complex64), 2 * rel_l2(want, ref))
 
 
+@pytest.mark.parametrize("n", [2049, 4099, 10007, 44100, 112501, 300000])
+def test_large_non_power_of_two(planner, n):
+    """Bluestein over a four-step inner FFT (beyond the reference's accuracy test range, which stops at
+    1000; 112501 is one of its 32-bit-overflow Rader primes, raders_algorithm.rs:311-322)."""
+    pl, dtype = planner
+    check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
+
+
 def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
     torch = torch_cuda
     pl = rb.FftPlanner(np.complex64)
-    for n, batch in [(1024, 33), (1 << 15, 70), (1 << 16, 5), (257, 9), (1000, 17)]:
+    for n, batch in [(1024, 33), (1 << 15, 70), (1 << 16, 5), (257, 9), (1000, 17), (65537, 40), (5000, 3)]:
         f = pl.plan_fft_forward(n)
         x = signal(n * batch, np.complex64, seed=n)
         host = x.copy()
