@@ -183,10 +183,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ws_bytes = max(plans[lg].workspace_bytes(BATCH) for lg in logs)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
 
-    def one_size(lg):
+    def one_size(lg, rep=0):
         n = 1 << lg
-        a = src[offs[lg]: offs[lg] + BATCH * n]
-        b = dst[offs[lg]: offs[lg] + BATCH * n]
+        o = offs[lg] if rep == 0 else (rep * BATCH * n) % max_elems
+        a = src[o: o + BATCH * n]
+        b = dst[o: o + BATCH * n]
         plans[lg].process_device(a, out=b, workspace=ws if plans[lg].workspace_bytes(BATCH) else None)
 
     def barrier():
@@ -200,6 +201,45 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             one_size(lg)
     barrier()
 
+    # Launch path: each size's exec is captured once into a CUDA graph and replayed, so the GPU never
+    # waits for the Python/ctypes launch path between kernels (the library issues up to ~1000 launches
+    # per exec for the chunked two-pass plans).  Falls back to plain stream launches if capture fails.
+    launch_mode = "cuda-graph replay (one graph per size)"
+    graphs, rep_graphs, reps = {}, {}, {}
+    if args.profile or args.no_graph:
+        launch_mode = "stream launches"
+    else:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for lg in logs:
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1, stream=side):
+                        one_size(lg)
+                    graphs[lg] = g1
+                    # supplementary per-size measurement: R back-to-back execs over R distinct regions (>= 2 GiB)
+                    reps[lg] = max(1, min(64, (1 << 31) // (8 * (BATCH << lg))))
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2, stream=side):
+                        for r in range(reps[lg]):
+                            one_size(lg, rep=r + 1 if reps[lg] > 1 else 0)
+                    rep_graphs[lg] = g2
+            torch.cuda.current_stream().wait_stream(side)
+        except Exception as e:  # pragma: no cover
+            launch_mode = f"stream launches (graph capture failed: {type(e).__name__})"
+            graphs, rep_graphs = {}, {}
+
+    def run_size(lg):
+        if graphs:
+            graphs[lg].replay()
+        else:
+            one_size(lg)
+
+    for lg in logs:  # one more warm-up through the final launch path
+        run_size(lg)
+    barrier()
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(logs) + 1)] for _ in range(args.steps)]
@@ -207,18 +247,34 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for s in range(args.steps):
         ev[s][0].record()
         for i, lg in enumerate(logs):
-            one_size(lg)
+            run_size(lg)
             ev[s][i + 1].record()
     barrier()
     clocks = sampler.stop()
     total_ms = ev[0][0].elapsed_time(ev[-1][-1])
     per_ms = {lg: sum(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) / args.steps
               for i, lg in enumerate(logs)}
+    # supplementary: per-size time from R back-to-back execs (amortises the ~10 us launch+drain of a single
+    # exec, which is comparable to the whole transform time at N = 2^10..2^12)
+    per_ms_rep = {}
+    if rep_graphs:
+        for lg in logs:
+            rep_graphs[lg].replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rep_graphs[lg].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            per_ms_rep[lg] = e0.elapsed_time(e1) / reps[lg]
     if dist:
-        t = torch.tensor([total_ms] + [per_ms[lg] for lg in logs], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms] + [per_ms[lg] for lg in logs] + [per_ms_rep.get(lg, 0.0) for lg in logs],
+                         device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t[0].item()
         per_ms = {lg: t[i + 1].item() for i, lg in enumerate(logs)}
+        if per_ms_rep:
+            per_ms_rep = {lg: t[i + 1 + len(logs)].item() for i, lg in enumerate(logs)}
 
     hbm, peak_src = peaks()
     step_ms = total_ms / args.steps
@@ -228,9 +284,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     per_size = []
     for lg in logs:
         gbs = 16.0 * (1 << lg) * BATCH / (per_ms[lg] * 1e-3) / 1e9
-        per_size.append({"log2n": lg, "plan": plans[lg].describe(), "ms": round(per_ms[lg], 4),
-                         "gflops": round(flops(1 << lg, BATCH) / (per_ms[lg] * 1e-3) / 1e9, 1),
-                         "gbs": round(gbs, 1), "frac": round(gbs / hbm, 4)})
+        row = {"log2n": lg, "plan": plans[lg].describe(), "ms": round(per_ms[lg], 4),
+               "gflops": round(flops(1 << lg, BATCH) / (per_ms[lg] * 1e-3) / 1e9, 1),
+               "gbs": round(gbs, 1), "frac": round(gbs / hbm, 4)}
+        if lg in per_ms_rep:
+            g2 = 16.0 * (1 << lg) * BATCH / (per_ms_rep[lg] * 1e-3) / 1e9
+            row.update({"back_to_back_reps": reps[lg], "ms_b2b": round(per_ms_rep[lg], 4), "gbs_b2b": round(g2, 1),
+                        "frac_b2b": round(g2 / hbm, 4)})
+        per_size.append(row)
     achieved = step_bytes / (step_ms * 1e-3) / 1e9
     launches = sum(plans[lg].launches(BATCH) for lg in logs) * args.steps
     traffic = None
@@ -293,6 +354,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: f32 forward, N=2^10..2^20, batch=4096 per GPU, out of place, "
                                    "device resident", "sizes_log2": logs, "batch_per_gpu": BATCH,
+                       "launch": launch_mode,
                        "l2_policy": "inputs larger than L2: each size has its own region of a 32 GiB buffer, "
                                     ">= 32 GiB of other traffic between two touches of any byte",
                        "per_size": per_size},
@@ -318,6 +380,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-pinned-gib", type=float, default=4.0)
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / cpu legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -5,10 +5,10 @@
 // Planner (what RustFFT's planners decide in src/plan.rs:412-665 / src/avx/avx_planner.rs:205-216,
 // re-decided for a GPU):
 //   len 0, 1                      -> Identity
-//   2^k <= DIRECT_MAX             -> Direct      one CTA pass, Stockham radix-4/8/16 in registers+smem
-//   2^k  > DIRECT_MAX (<= 2^20)   -> FourStep    two passes, intermediate kept in L2 by chunking
-//   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= DIRECT_MAX)
-//   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= DIRECT_MAX)
+//   2^k <= 16384 (f64: 8192)      -> Direct      one CTA pass, Stockham radix-4/8/16 in registers+smem
+//   larger 2^k (<= 2^20)          -> FourStep    two passes, intermediate kept in L2 by chunking
+//   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= 256, else over FourStep)
+//   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= 4096)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +51,8 @@ B2_DIRECT(float, 512, 16, 8, 2, 16, 16)
 B2_DIRECT(float, 1024, 16, 4, 4, 16, 16)
 B2_DIRECT(float, 2048, 16, 2, 8, 16, 16)
 B2_DIRECT(float, 4096, 16, 1, 16, 16, 16)
+B2_DIRECT(float, 8192, 16, 1, 2, 16, 16, 16)
+B2_DIRECT(float, 16384, 16, 1, 4, 16, 16, 16)
 
 B2_DIRECT(double, 2, 2, 128, 2)
 B2_DIRECT(double, 4, 4, 128, 4)
@@ -64,6 +66,7 @@ B2_DIRECT(double, 512, 8, 4, 8, 8, 8)
 B2_DIRECT(double, 1024, 8, 2, 2, 8, 8, 8)
 B2_DIRECT(double, 2048, 8, 1, 4, 8, 8, 8)
 B2_DIRECT(double, 4096, 8, 1, 8, 8, 8, 8)
+B2_DIRECT(double, 8192, 8, 1, 2, 8, 8, 8, 8)
 
 B2_TILE(float, 64, 8, 16, 8, 8)
 B2_TILE(float, 128, 16, 16, 8, 16)
@@ -77,7 +80,9 @@ B2_TILE(double, 256, 8, 8, 4, 8, 8)
 B2_TILE(double, 512, 8, 8, 8, 8, 8)
 B2_TILE(double, 1024, 8, 4, 2, 8, 8, 8)
 
-static constexpr uint32_t DIRECT_MAX = 4096;
+// largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
+template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
+static constexpr uint32_t FUSED_CONV_MAX = 4096;  // largest inner FFT of the fused Bluestein / Rader kernels
 static constexpr uint32_t TILE_MIN = 64, TILE_MAX = 1024;
 
 // ---- plan object ----------------------------------------------------------------------------
@@ -137,7 +142,7 @@ static uint64_t chunk_bytes() {
     // target footprint of the L2-resident intermediate of multi-pass plans (B200 L2: ~126 MB)
     static uint64_t v = [] {
         const char* e = std::getenv("B200FFT_CHUNK_MB");
-        uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 32;
+        uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 64;
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
@@ -188,6 +193,9 @@ struct Builder {
             case 1024: return make_direct<1024>(pl);
             case 2048: return make_direct<2048>(pl);
             case 4096: return make_direct<4096>(pl);
+            case 8192: return make_direct<8192>(pl);
+            case 16384:
+                if constexpr (sizeof(T) == 4) return make_direct<16384>(pl);
         }
         return false;
     }
@@ -582,7 +590,7 @@ struct Builder {
         }
         bool ok = false;
         if (hm::is_pow2(n)) {
-            if (n <= DIRECT_MAX)
+            if (n <= DirectMax<T>::v)
                 ok = make_direct_rt(pl, (uint32_t)n);
             else if (n <= (uint64_t)TILE_MAX * TILE_MAX)
                 ok = make_four_step(pl, hm::ilog2(n));
@@ -594,7 +602,7 @@ struct Builder {
             ok = make_big_conv(pl, n - 1, true);  // 65537
         } else {
             const uint64_t M = hm::next_pow2(2 * n - 1);
-            if (M <= DIRECT_MAX)
+            if (M <= FUSED_CONV_MAX)
                 ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
             else if (M <= (uint64_t)TILE_MAX * TILE_MAX)
                 ok = make_big_conv(pl, M, false);

@@ -23,6 +23,8 @@
 
 namespace b2 {
 
+constexpr int default_min_blocks(int nt) { return nt >= 1024 ? 1 : (nt >= 512 ? 2 : (nt >= 256 ? 3 : 4)); }
+
 // ------------------------------------------------------------------------------------------
 // Functors.  prep(g, ok) is evaluated once per thread (g = global FFT index of this thread's
 // FFT, ok = g is inside the launch), get/put once per element.
@@ -209,6 +211,7 @@ struct FftKernel {
     using T = typename G::T;
     using Eng = Engine<G, M0, M1>;
     static constexpr int NT = G::NT;
+    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT);
     static constexpr int NPHASE = Eng::NPHASE;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
     struct Params {
@@ -250,6 +253,7 @@ struct BluesteinKernel {
     using T = typename G::T;
     using Eng = Engine<G, JF, JF>;
     static constexpr int NT = G::NT;
+    static constexpr int MIN_BLOCKS = 1;  // two FFTs inlined back to back: let it have the registers
     static constexpr int NP1 = Eng::NPHASE;
     static constexpr int NPHASE = 2 * NP1 - 1;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
@@ -324,6 +328,7 @@ struct RaderKernel {
     using T = typename G::T;
     using Eng = Engine<G, JF, JF>;
     static constexpr int NT = G::NT;
+    static constexpr int MIN_BLOCKS = 1;  // two FFTs inlined back to back: let it have the registers
     static constexpr int NP1 = Eng::NPHASE;
     static constexpr int NPHASE = 2 * NP1 - 1;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
@@ -412,8 +417,11 @@ struct PhaseRunner {
 };
 
 #if defined(__CUDACC__)
+// minimum CTAs per SM the register allocator must leave room for: 512-thread CTAs would otherwise take
+// > 64 registers and run alone on an SM (measured round 1: 1 CTA/SM, 25 % occupancy on the 1024-point tiles)
+
 template <class KT>
-__global__ void __launch_bounds__(KT::NT) run_kernel(const __grid_constant__ typename KT::Params p) {
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel(const __grid_constant__ typename KT::Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));

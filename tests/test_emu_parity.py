@@ -38,13 +38,15 @@ def test_sampled_lens_up_to_1000_and_plan_kinds(planner):
     assert {"Direct", "Bluestein", "Rader"} <= seen
 
 
-@pytest.mark.parametrize("n,desc", [(2048, "Direct{2048}"), (4096, "Direct{4096}"), (8192, "FourStep{64x128}"),
-                                    (1 << 14, "FourStep{128x128}"), (1 << 15, "FourStep{128x256}"),
-                                    (1 << 16, "FourStep{256x256}"), (1 << 17, "FourStep{256x512}")])
-def test_power_of_two_plans(planner, n, desc):
+@pytest.mark.parametrize("n,desc32,desc64", [
+    (2048, "Direct{2048}", "Direct{2048}"), (4096, "Direct{4096}", "Direct{4096}"),
+    (8192, "Direct{8192}", "Direct{8192}"), (1 << 14, "Direct{16384}", "FourStep{128x128}"),
+    (1 << 15, "FourStep{128x256}", "FourStep{128x256}"), (1 << 16, "FourStep{256x256}", "FourStep{256x256}"),
+    (1 << 17, "FourStep{256x512}", "FourStep{256x512}")])
+def test_power_of_two_plans(planner, n, desc32, desc64):
     pl, dtype = planner
     f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
-    assert f.describe() == desc
+    assert f.describe() == (desc32 if dtype == np.complex64 else desc64)
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
@@ -67,13 +69,14 @@ def test_large_convolution_plans(planner, n, desc):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
-def test_chunked_four_step_matches_unchunked(lib, monkeypatch):
-    # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk
+def test_chunked_four_step_matches_unchunked(lib):
+    # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk (the emulation
+    # library is loaded with B200FFT_CHUNK_MB=32, tests/util.py)
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 1 << 16, 70
     x = signal(n * batch, np.complex64, seed=5)
     f = pl.plan_fft_forward(n)
-    assert f.launches(batch) == 4 and f.workspace_bytes(batch) == 64 * n * 8
+    assert f.launches(batch) == 4 and f.workspace_bytes(batch) == 64 * n * 8  # B200FFT_CHUNK_MB=32, see fixture
     y = x.copy()
     f.process(y)
     for b in (0, 63, 64, 69):

@@ -132,7 +132,7 @@ def test_large_non_power_of_two(planner, n):
 def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
     torch = torch_cuda
     pl = rb.FftPlanner(np.complex64)
-    for n, batch in [(1024, 33), (1 << 15, 70), (1 << 16, 5), (257, 9), (1000, 17), (65537, 40), (5000, 3)]:
+    for n, batch in [(1024, 33), (1 << 14, 5), (1 << 15, 300), (1 << 16, 5), (257, 9), (1000, 17), (65537, 80), (5000, 3)]:
         f = pl.plan_fft_forward(n)
         x = signal(n * batch, np.complex64, seed=n)
         host = x.copy()
@@ -164,8 +164,8 @@ def test_shared_plan_from_many_threads(torch_cuda):
     """examples/concurrency.rs:17-29: one Arc<dyn Fft> used by several threads at once."""
     torch = torch_cuda
     pl = rb.FftPlanner(np.complex64)
-    f = pl.plan_fft_forward(1 << 14)  # FourStep: needs a per-call workspace
-    n = 1 << 14
+    f = pl.plan_fft_forward(1 << 15)  # FourStep: needs a per-call workspace
+    n = 1 << 15
     xs = [signal(n * 8, np.complex64, seed=t) for t in range(6)]
     outs = [None] * 6
 
@@ -190,7 +190,8 @@ def test_shared_plan_from_many_threads(torch_cuda):
 def test_ragged_batches_and_tails(torch_cuda):
     """batch sizes that do not fill the last CTA (F transforms per CTA) or the last L2 chunk."""
     pl = rb.FftPlanner(np.complex64)
-    for n, batches in [(8, [1, 127, 129]), (64, [1, 15, 17]), (256, [1, 7, 9]), (1 << 13, [1, 3]), (100, [1, 15, 17])]:
+    for n, batches in [(8, [1, 127, 129]), (64, [1, 15, 17]), (256, [1, 7, 9]), (1 << 13, [1, 3]), (1 << 15, [1, 3]),
+                       (100, [1, 15, 17])]:
         f = pl.plan_fft_forward(n)
         for b in batches:
             x = signal(n * b, np.complex64, seed=b)

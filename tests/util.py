@@ -47,4 +47,5 @@ def emu_library():
     import __graft_entry__ as ge
     import rustfft_b200 as rb
 
+    os.environ.setdefault("B200FFT_CHUNK_MB", "32")  # read once by the library; pins the chunking the tests assert
     return rb.Library(ge.build_emu())
