@@ -14,8 +14,8 @@
 // followed by layers of twiddled radix-r cross butterflies -- but auto-sorting, so there is no
 // digit-reversal pass (src/array_utils.rs:372-437) and natural order falls out of the last stage.
 //
-// Shared-memory layout: sidx(f, e) = f*LP + e + (e >> 4) with LP odd.  The 1-in-16 pad makes the
-// stride-R scatter of a stage conflict free for 8-byte accesses, the odd pitch makes "f fastest"
+// Shared-memory layout: sidx(f, e) = f*LP + e + (e >> 4).  The 1-in-16 pad makes the stride-R
+// scatter of a stage conflict free for 8-byte accesses, the row pitch LP (see Geo) makes "f fastest"
 // thread mappings (strided-column tiles) conflict free; see tests/test_engine_model.py.
 #pragma once
 #include "butterfly.h"
@@ -34,7 +34,12 @@ struct Geo {
     static constexpr int NT = F * TP;  // threads per CTA
     static constexpr int NS = RL::N;   // stages
     static constexpr int LPAD = L + (PS ? (L >> PS) : 0);
-    static constexpr int LP = (F > 1) ? (LPAD | 1) : LPAD;
+    // row pitch between the F FFTs of a CTA: a multiple of one 128-byte bank sweep plus UNIT/F elements
+    // (plus 1 when F >= UNIT), so that the F (or UNIT) consecutive FFTs a transaction touches in the
+    // "f fastest" mapping start on different bank groups -- tests/test_engine_model.py
+    static constexpr int UNIT = 128 / (2 * (int)sizeof(T_));
+    static constexpr int LPR = (LPAD + UNIT - 1) / UNIT * UNIT;
+    static constexpr int LP = (F <= 1) ? LPAD : (F >= UNIT ? LPR + 1 : LPR + UNIT / F);
     static constexpr int SMEM_ELEMS = (NS > 1) ? F * LP : 0;
     static constexpr int TW_ELEMS = RL::tw_total();
     static B2_HD int sidx(int f, int e) { return f * LP + e + (PS ? (e >> PS) : 0); }

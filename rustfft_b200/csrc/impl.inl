@@ -72,7 +72,9 @@ B2_TILE(float, 64, 8, 16, 8, 8)
 B2_TILE(float, 128, 16, 16, 8, 16)
 B2_TILE(float, 256, 16, 16, 16, 16)
 B2_TILE(float, 512, 16, 16, 2, 16, 16)
-B2_TILE(float, 1024, 16, 8, 4, 16, 16)
+B2_TILE(float, 1024, 16, 8, 16, 16, 4)
+// tuning variant (B200FFT_TILE1024=16): 16-wide 1024-point tiles, one 1024-thread CTA per SM
+template <> struct TileGeo<float, 1025> { using type = Geo<float, 1024, 16, 16, Radices<4, 16, 16>>; };
 
 B2_TILE(double, 64, 8, 16, 8, 8)
 B2_TILE(double, 128, 8, 16, 2, 8, 8)
@@ -149,6 +151,14 @@ static uint64_t chunk_bytes() {
     return v;
 }
 
+static bool tile1024_wide() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_TILE1024");
+        return e && std::atoi(e) == 16;
+    }();
+    return v;
+}
+
 template <typename T>
 struct Builder {
     typedef cx<T> C;
@@ -209,15 +219,15 @@ struct Builder {
         std::function<bool(const C* work, C* out, uint64_t nb, rt::stream_t)> b;
     };
     template <int L1, bool SW>
-    static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, TwoLevelTw<T> tl, PassFns& fns) {
+    static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, PassFns& fns) {
         using G = typename TileGeo<T, L1>::type;
-        using KT = FftKernel<G, FF, FF, LoadCols<T, SW>, StoreColsTw<T>>;
+        using KT = FftKernel<G, FF, FF, LoadCols<T, SW>, StoreCols<T>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         fns.a = [=](const C* in, C* work, uint64_t nb, rt::stream_t s) {
             typename KT::Params p;
             p.load = LoadCols<T, SW>{in, lgN, lg2};
-            p.store = StoreColsTw<T>{work, lgN, lg2, tl};
+            p.store = StoreCols<T>{work, lgN, lg2};
             p.tw = tw;
             p.n_fft = nb << lg2;
             return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
@@ -225,14 +235,14 @@ struct Builder {
         return true;
     }
     template <int L2, bool SW>
-    static bool make_pass_b(b200fft_plan& pl, uint32_t lgN, uint32_t lg1, PassFns& fns) {
+    static bool make_pass_b(b200fft_plan& pl, uint32_t lgN, uint32_t lg1, const C* full_tw, PassFns& fns) {
         using G = typename TileGeo<T, L2>::type;
-        using KT = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposed<T, SW>>;
+        using KT = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposed<T, SW>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         fns.b = [=](const C* work, C* out, uint64_t nb, rt::stream_t s) {
             typename KT::Params p;
-            p.load = LoadRows<T, false>{work, (uint32_t)L2};
+            p.load = LoadRowsTw<T>{work, full_tw, (uint32_t)G::L, lg1};
             p.store = StoreTransposed<T, SW>{out, lgN, lg1};
             p.tw = tw;
             p.n_fft = nb << lg1;
@@ -241,48 +251,53 @@ struct Builder {
         return true;
     }
     template <bool SW>
-    static bool make_pass_a_rt(b200fft_plan& pl, uint32_t L1, uint32_t lgN, uint32_t lg2, TwoLevelTw<T> tl, PassFns& f) {
+    static bool make_pass_a_rt(b200fft_plan& pl, uint32_t L1, uint32_t lgN, uint32_t lg2, PassFns& f) {
         switch (L1) {
-            case 64: return make_pass_a<64, SW>(pl, lgN, lg2, tl, f);
-            case 128: return make_pass_a<128, SW>(pl, lgN, lg2, tl, f);
-            case 256: return make_pass_a<256, SW>(pl, lgN, lg2, tl, f);
-            case 512: return make_pass_a<512, SW>(pl, lgN, lg2, tl, f);
-            case 1024: return make_pass_a<1024, SW>(pl, lgN, lg2, tl, f);
+            case 64: return make_pass_a<64, SW>(pl, lgN, lg2, f);
+            case 128: return make_pass_a<128, SW>(pl, lgN, lg2, f);
+            case 256: return make_pass_a<256, SW>(pl, lgN, lg2, f);
+            case 512: return make_pass_a<512, SW>(pl, lgN, lg2, f);
+            case 1024:
+                if constexpr (sizeof(T) == 4) {
+                    if (tile1024_wide()) return make_pass_a<1025, SW>(pl, lgN, lg2, f);
+                }
+                return make_pass_a<1024, SW>(pl, lgN, lg2, f);
         }
         return false;
     }
     template <bool SW>
-    static bool make_pass_b_rt(b200fft_plan& pl, uint32_t L2, uint32_t lgN, uint32_t lg1, PassFns& f) {
+    static bool make_pass_b_rt(b200fft_plan& pl, uint32_t L2, uint32_t lgN, uint32_t lg1, const C* tw, PassFns& f) {
         switch (L2) {
-            case 64: return make_pass_b<64, SW>(pl, lgN, lg1, f);
-            case 128: return make_pass_b<128, SW>(pl, lgN, lg1, f);
-            case 256: return make_pass_b<256, SW>(pl, lgN, lg1, f);
-            case 512: return make_pass_b<512, SW>(pl, lgN, lg1, f);
-            case 1024: return make_pass_b<1024, SW>(pl, lgN, lg1, f);
+            case 64: return make_pass_b<64, SW>(pl, lgN, lg1, tw, f);
+            case 128: return make_pass_b<128, SW>(pl, lgN, lg1, tw, f);
+            case 256: return make_pass_b<256, SW>(pl, lgN, lg1, tw, f);
+            case 512: return make_pass_b<512, SW>(pl, lgN, lg1, tw, f);
+            case 1024:
+                if constexpr (sizeof(T) == 4) {
+                    if (tile1024_wide()) return make_pass_b<1025, SW>(pl, lgN, lg1, tw, f);
+                }
+                return make_pass_b<1024, SW>(pl, lgN, lg1, tw, f);
         }
         return false;
     }
-    static bool make_two_level(b200fft_plan& pl, uint32_t lgN, TwoLevelTw<T>& tl) {
-        const uint32_t lgS = (lgN + 1) / 2;
-        const uint64_t N = 1ull << lgN, S = 1ull << lgS;
-        std::vector<C> a((size_t)S), b((size_t)(N >> lgS));
-        for (uint64_t i = 0; i < S; ++i) a[(size_t)i] = hm::twiddle<T>(i, N);
-        for (uint64_t i = 0; i < (N >> lgS); ++i) b[(size_t)i] = hm::twiddle<T>(i << lgS, N);
-        tl.a = upload(pl, a);
-        tl.b = upload(pl, b);
-        tl.lgS = lgS;
-        return tl.a && tl.b;
+    // inter-pass twiddles W_N^(k1*n2), laid out [k1][n2] (N entries)
+    static const C* make_full_twiddles(b200fft_plan& pl, uint32_t lg1, uint32_t lg2) {
+        const uint64_t N1 = 1ull << lg1, N2 = 1ull << lg2, N = N1 * N2;
+        std::vector<C> t((size_t)N);
+        for (uint64_t k1 = 0; k1 < N1; ++k1)
+            for (uint64_t n2 = 0; n2 < N2; ++n2) t[(size_t)(k1 * N2 + n2)] = hm::twiddle<T>(k1 * n2, N);
+        return upload(pl, t);
     }
     static bool make_four_step(b200fft_plan& pl, uint32_t lgN) {
         const uint32_t lg1 = lgN / 2, lg2 = lgN - lg1;  // N1 <= N2
         const uint32_t N1 = 1u << lg1, N2 = 1u << lg2;
         if (N1 < TILE_MIN || N2 > TILE_MAX) return false;
-        TwoLevelTw<T> tl;
-        if (!make_two_level(pl, lgN, tl)) return false;
+        const C* full_tw = make_full_twiddles(pl, lg1, lg2);
+        if (!full_tw) return false;
         PassFns fns;
         const bool sw = pl.direction != 0;
-        const bool ok_a = sw ? make_pass_a_rt<true>(pl, N1, lgN, lg2, tl, fns) : make_pass_a_rt<false>(pl, N1, lgN, lg2, tl, fns);
-        const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, fns);
+        const bool ok_a = sw ? make_pass_a_rt<true>(pl, N1, lgN, lg2, fns) : make_pass_a_rt<false>(pl, N1, lgN, lg2, fns);
+        const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
         const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / (N * sizeof(C)));
@@ -313,6 +328,7 @@ struct Builder {
         const uint32_t* scatter = nullptr;  // Rader: g^-(i+1) mod n
         const C* chirp = nullptr;           // Bluestein: W_2n^(i^2)
         const C* mult = nullptr;            // M entries
+        const C* full_tw = nullptr;         // inner four-step twiddles [N1][N2]
         uint32_t n = 0, lgM = 0, lg1 = 0, lg2 = 0;
         bool rader = false;
     };
@@ -322,15 +338,15 @@ struct Builder {
         std::function<bool(const C* w2, C* out, uint64_t nb, rt::stream_t)> b2;
     };
     template <int L1, bool SW>
-    static bool make_conv_a1(b200fft_plan& pl, const ConvTables& t, TwoLevelTw<T> tl, ConvFns& f) {
+    static bool make_conv_a1(b200fft_plan& pl, const ConvTables& t, ConvFns& f) {
         using G = typename TileGeo<T, L1>::type;
-        using KT = FftKernel<G, FF, FF, LoadColsConv<T, SW>, StoreColsTw<T>>;
+        using KT = FftKernel<G, FF, FF, LoadColsConv<T, SW>, StoreCols<T>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         f.a1 = [=](const C* in, C* w1, uint64_t nb, rt::stream_t s) {
             typename KT::Params p;
             p.load = LoadColsConv<T, SW>{in, t.gather, t.chirp, t.n, t.lg2};
-            p.store = StoreColsTw<T>{w1, t.lgM, t.lg2, tl};
+            p.store = StoreCols<T>{w1, t.lgM, t.lg2};
             p.tw = tw;
             p.n_fft = nb << t.lg2;
             return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
@@ -340,32 +356,32 @@ struct Builder {
     template <int L2, bool SW>
     static bool make_conv_b(b200fft_plan& pl, const ConvTables& t, ConvFns& f) {
         using G = typename TileGeo<T, L2>::type;
-        using K0 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 0>>;
+        using K0 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 0>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         f.b1 = [=](const C* w1, C* w2, const C* in, C* out, uint64_t nb, rt::stream_t s) {
             typename K0::Params p;
-            p.load = LoadRows<T, false>{w1, (uint32_t)L2};
+            p.load = LoadRowsTw<T>{w1, t.full_tw, (uint32_t)L2, t.lg1};
             p.store = StoreTransposedConv<T, SW, 0>{w2, t.mult, nullptr, nullptr, t.rader ? in : nullptr, out, t.n, t.lgM, t.lg1};
             p.tw = tw;
             p.n_fft = nb << t.lg1;
             return rt::launch<K0>(p, (p.n_fft + G::F - 1) / G::F, s);
         };
         if (t.rader) {
-            using K1 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 1>>;
+            using K1 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 1>>;
             f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
                 typename K1::Params p;
-                p.load = LoadRows<T, false>{w2, (uint32_t)L2};
+                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)L2, t.lg1};
                 p.store = StoreTransposedConv<T, SW, 1>{out, nullptr, t.scatter, nullptr, nullptr, nullptr, t.n, t.lgM, t.lg1};
                 p.tw = tw;
                 p.n_fft = nb << t.lg1;
                 return rt::launch<K1>(p, (p.n_fft + G::F - 1) / G::F, s);
             };
         } else {
-            using K2 = FftKernel<G, JF, FF, LoadRows<T, false>, StoreTransposedConv<T, SW, 2>>;
+            using K2 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 2>>;
             f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
                 typename K2::Params p;
-                p.load = LoadRows<T, false>{w2, (uint32_t)L2};
+                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)L2, t.lg1};
                 p.store = StoreTransposedConv<T, SW, 2>{out, nullptr, nullptr, t.chirp, nullptr, nullptr, t.n, t.lgM, t.lg1};
                 p.tw = tw;
                 p.n_fft = nb << t.lg1;
@@ -375,14 +391,14 @@ struct Builder {
         return true;
     }
     template <bool SW>
-    static bool make_conv_rt(b200fft_plan& pl, const ConvTables& t, TwoLevelTw<T> tl, ConvFns& f, PassFns& plain) {
+    static bool make_conv_rt(b200fft_plan& pl, const ConvTables& t, ConvFns& f, PassFns& plain) {
         bool ok = false;
         switch (1u << t.lg1) {
-            case 64: ok = make_conv_a1<64, SW>(pl, t, tl, f) && make_pass_a<64, false>(pl, t.lgM, t.lg2, tl, plain); break;
-            case 128: ok = make_conv_a1<128, SW>(pl, t, tl, f) && make_pass_a<128, false>(pl, t.lgM, t.lg2, tl, plain); break;
-            case 256: ok = make_conv_a1<256, SW>(pl, t, tl, f) && make_pass_a<256, false>(pl, t.lgM, t.lg2, tl, plain); break;
-            case 512: ok = make_conv_a1<512, SW>(pl, t, tl, f) && make_pass_a<512, false>(pl, t.lgM, t.lg2, tl, plain); break;
-            case 1024: ok = make_conv_a1<1024, SW>(pl, t, tl, f) && make_pass_a<1024, false>(pl, t.lgM, t.lg2, tl, plain); break;
+            case 64: ok = make_conv_a1<64, SW>(pl, t, f) && make_pass_a<64, false>(pl, t.lgM, t.lg2, plain); break;
+            case 128: ok = make_conv_a1<128, SW>(pl, t, f) && make_pass_a<128, false>(pl, t.lgM, t.lg2, plain); break;
+            case 256: ok = make_conv_a1<256, SW>(pl, t, f) && make_pass_a<256, false>(pl, t.lgM, t.lg2, plain); break;
+            case 512: ok = make_conv_a1<512, SW>(pl, t, f) && make_pass_a<512, false>(pl, t.lgM, t.lg2, plain); break;
+            case 1024: ok = make_conv_a1<1024, SW>(pl, t, f) && make_pass_a<1024, false>(pl, t.lgM, t.lg2, plain); break;
         }
         if (!ok) return false;
         switch (1u << t.lg2) {
@@ -420,11 +436,11 @@ struct Builder {
         }
         t.mult = upload(pl, mult);
         if (!t.mult) return false;
-        TwoLevelTw<T> tl;
-        if (!make_two_level(pl, t.lgM, tl)) return false;
+        t.full_tw = make_full_twiddles(pl, t.lg1, t.lg2);
+        if (!t.full_tw) return false;
         ConvFns f;
         PassFns plain;
-        const bool ok = pl.direction ? make_conv_rt<true>(pl, t, tl, f, plain) : make_conv_rt<false>(pl, t, tl, f, plain);
+        const bool ok = pl.direction ? make_conv_rt<true>(pl, t, f, plain) : make_conv_rt<false>(pl, t, f, plain);
         if (!ok) return false;
         const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / 2 / (M * sizeof(C)));
         pl.work_bytes = [=](uint64_t batch) { return 2 * std::min(batch, chunk) * M * sizeof(C); };

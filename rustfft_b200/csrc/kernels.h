@@ -3,10 +3,10 @@
 //
 //   FftKernel<G, M0, M1, Load, Store>   one FFT pass: Load -> L-point FFT -> Store
 //       Load = LoadRows,  Store = StoreRows            whole transform in one CTA pass  (N = L)
-//       Load = LoadCols,  Store = StoreColsTw          four-step pass A: strided column FFTs of
-//                                                      length N1, times W_N^(n2*k1), in place
-//       Load = LoadRows,  Store = StoreTransposed      four-step pass B: contiguous row FFTs of
-//                                                      length N2, written back transposed
+//       Load = LoadCols,  Store = StoreCols            four-step pass A: strided column FFTs of
+//                                                      length N1, in place
+//       Load = LoadRowsTw, Store = StoreTransposed     four-step pass B: contiguous rows times
+//                                                      W_N^(n2*k1), N2-point FFT, written transposed
 //   (four-step == the reference's six-step MixedRadix, src/algorithm/mixed_radix.rs:128-158, with
 //    its three transposes folded into the strided loads/stores of the two passes)
 //
@@ -72,36 +72,42 @@ struct LoadCols {
     }
 };
 
-// two-level twiddle W_N^m = A[m & (S-1)] * B[m >> lgS]: both tables are rounded from a
-// long-double evaluation, so the product carries <= 1.5 ulp instead of a table of N entries per
-// size (for N = 2^20 that table alone would be 8 MiB of L2 traffic per pass)
+// four-step pass A store: out[b*N + k1*N2 + c] = v  (the slots the tile was read from, so the pass is in
+// place per tile; plain write-back stores: pass B re-reads them from L2)
 template <typename T>
-struct TwoLevelTw {
-    const cx<T>* a;  // W_N^i,        i < S = 1 << lgS
-    const cx<T>* b;  // W_N^(S*i),    i < N / S
-    uint32_t lgS;
-    B2_HD cx<T> at(uint32_t m) const {
-        const cx<T> lo = ldg(a + (m & ((1u << lgS) - 1)));
-        const cx<T> hi = ldg(b + (m >> lgS));
-        return cmul(lo, hi);
+struct StoreCols {
+    cx<T>* out;
+    uint32_t lgN, lg2;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = g >> lg2, c = g & ((1ull << lg2) - 1);
+        return St{out + (b << lgN) + c, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) s.p[(uint32_t)e << lg2] = v;
     }
 };
 
-// four-step pass A store: out[b*N + k1*N2 + c] = v * W_N^(c*k1)   (same slots the tile was read
-// from, so the pass is in place per tile; plain write-back stores: the next pass re-reads from L2)
+// four-step pass B load: row k1 of transform b (FFT g = b*N1 + k1), element n2 = e, times the inter-pass
+// twiddle W_N^(k1*n2) from a full [k1][n2] table (N entries, each rounded once from long double --
+// the reference's MixedRadix keeps the same N-entry table, src/algorithm/mixed_radix.rs:66-71).
+// The table is applied HERE rather than on pass A's store because this side is contiguous: table and
+// data are both read as 256-byte-per-warp streams (round 1 measured the earlier two-level gather on the
+// strided side as the LSU-pipe bottleneck of pass A).
 template <typename T>
-struct StoreColsTw {
-    cx<T>* out;
-    uint32_t lgN, lg2;
-    TwoLevelTw<T> tw;
-    struct St { cx<T>* p; uint32_t c; bool ok; };
+struct LoadRowsTw {
+    const cx<T>* in;
+    const cx<T>* tw;  // [N1][N2]
+    uint32_t len;     // N2
+    uint32_t lg1;     // log2 N1
+    struct St { const cx<T>* p; const cx<T>* t; bool ok; };
     B2_HD St prep(uint64_t g, bool ok) const {
-        const uint64_t b = g >> lg2, c = g & ((1ull << lg2) - 1);
-        return St{out + (b << lgN) + c, (uint32_t)c, ok};
+        const uint64_t k1 = g & ((1ull << lg1) - 1);
+        return St{in + g * (uint64_t)len, tw + k1 * (uint64_t)len, ok};
     }
-    B2_HD void put(const St& s, int e, cx<T> v) const {
-        if (!s.ok) return;
-        s.p[(uint32_t)e << lg2] = cmul(v, tw.at(s.c * (uint32_t)e));
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        return cmul(ld_stream(s.p + e), ldg(s.t + e));
     }
 };
 

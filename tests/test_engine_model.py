@@ -72,9 +72,11 @@ def _degree(addrs, elem_words):
 def _worst_conflict(L, radices, E, F, maps, PS=4, elem_words=2):
     T = L // E
     NT = F * T
+    unit = 32 // elem_words  # elements per 128-byte bank sweep
     LP = L + (L >> PS)
-    if F > 1:
-        LP |= 1
+    if F > 1:  # Geo::LP in engine.h
+        LPR = (LP + unit - 1) // unit * unit
+        LP = LPR + 1 if F >= unit else LPR + unit // F
     sidx = lambda f, e: (f * LP + e + (e >> PS)) * elem_words
     worst, p = 1, 1
     for s, R in enumerate(radices):
@@ -102,6 +104,7 @@ def _worst_conflict(L, radices, E, F, maps, PS=4, elem_words=2):
     (1024, [4, 16, 16], 16, 4, ["JF"] * 3), (512, [2, 16, 16], 16, 8, ["JF"] * 3), (256, [16, 16], 16, 8, ["JF"] * 2),
     (256, [16, 16], 16, 16, ["FF"] * 2), (512, [2, 16, 16], 16, 16, ["FF"] * 3),          # four-step pass A tiles
     (256, [16, 16], 16, 16, ["JF", "FF"]), (512, [2, 16, 16], 16, 16, ["JF", "FF", "FF"]),  # pass B tiles
+    (1024, [16, 16, 4], 16, 8, ["FF"] * 3), (1024, [16, 16, 4], 16, 8, ["JF", "FF", "FF"]),  # 8-wide 1024-point tiles
 ])
 def test_smem_layout_is_conflict_free_f32(L, radices, E, F, maps):
     assert _worst_conflict(L, radices, E, F, maps) == 1
