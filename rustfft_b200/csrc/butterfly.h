@@ -37,20 +37,19 @@ template <typename T> B2_HD void bf2(cx<T>& a, cx<T>& b) {
 
 // v0..v3 natural in/out
 template <typename T> B2_HD void bf4(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3) {
-    cx<T> t0 = v0 + v2, t1 = v0 - v2, t2 = v1 + v3, t3 = mul_mi(v1 - v3);
+    cx<T> t0 = v0 + v2, t1 = v0 - v2, t2 = v1 + v3, d = v1 - v3;
     v0 = t0 + t2;
-    v1 = t1 + t3;
+    v1 = add_mi(t1, d);  // t1 + (-i) d
     v2 = t0 - t2;
-    v3 = t1 - t3;
+    v3 = sub_mi(t1, d);
 }
 
 template <typename T> B2_HD void bf3(cx<T>& v0, cx<T>& v1, cx<T>& v2) {
-    cx<T> s = v1 + v2, d = v1 - v2;
-    cx<T> m = mk<T>(v0.x + K<T>::c3 * s.x, v0.y + K<T>::c3 * s.y);
-    cx<T> r = mk<T>(K<T>::s3 * d.y, -K<T>::s3 * d.x);  // -i*s3*d
+    cx<T> s = v1 + v2, d = scale(v1 - v2, K<T>::s3);
+    cx<T> m = axpy(v0, K<T>::c3, s);
     v0 = v0 + s;
-    v1 = m + r;
-    v2 = m - r;
+    v1 = add_mi(m, d);  // m + (-i) s3 d
+    v2 = sub_mi(m, d);
 }
 
 template <typename T> B2_HD void bf5(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3, cx<T>& v4) {
@@ -88,26 +87,22 @@ B2_HD void bf7(cx<T>& v0, cx<T>& v1, cx<T>& v2, cx<T>& v3, cx<T>& v4, cx<T>& v5,
     v4 = m3 - r3;
 }
 
-// multiply by W8^1 = (1-i)/sqrt2 and W8^3 = (-1-i)/sqrt2
-template <typename T> B2_HD cx<T> mul_w8_1(cx<T> a) {
-    return mk<T>((a.x + a.y) * K<T>::rsqrt2, (a.y - a.x) * K<T>::rsqrt2);
-}
-template <typename T> B2_HD cx<T> mul_w8_3(cx<T> a) {
-    return mk<T>((a.y - a.x) * K<T>::rsqrt2, -(a.x + a.y) * K<T>::rsqrt2);
-}
+// multiply by W8^1 = (1-i)/sqrt2 = (a + (-i)a)/sqrt2   and   W8^3 = (-1-i)/sqrt2 = -(a - (-i)a)/sqrt2
+template <typename T> B2_HD cx<T> mul_w8_1(cx<T> a) { return scale(add_mi(a, a), K<T>::rsqrt2); }
+template <typename T> B2_HD cx<T> mul_w8_3(cx<T> a) { return scale(sub_mi(a, a), -K<T>::rsqrt2); }
 
 template <typename T> B2_HD void bf8(cx<T> (&v)[8]) {
     // DIT: evens / odds 4-point, odd outputs twiddled by W8^k
     bf4(v[0], v[2], v[4], v[6]);
     bf4(v[1], v[3], v[5], v[7]);
-    cx<T> o1 = mul_w8_1(v[3]), o2 = mul_mi(v[5]), o3 = mul_w8_3(v[7]);
+    cx<T> o1 = mul_w8_1(v[3]), o2 = v[5], o3 = mul_w8_3(v[7]);
     cx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
     v[0] = e0 + o0;
     v[4] = e0 - o0;
     v[1] = e1 + o1;
     v[5] = e1 - o1;
-    v[2] = e2 + o2;
-    v[6] = e2 - o2;
+    v[2] = add_mi(e2, o2);  // W8^2 = -i
+    v[6] = sub_mi(e2, o2);
     v[3] = e3 + o3;
     v[7] = e3 - o3;
 }

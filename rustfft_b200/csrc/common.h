@@ -32,19 +32,106 @@ struct alignas(2 * sizeof(T)) cx {
 };
 
 template <typename T> B2_HD cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
-template <typename T> B2_HD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
-template <typename T> B2_HD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
-// (a.x + i a.y)(w.x + i w.y); compiles to 2 mul + 2 fma
+
+// ---- packed f32x2 arithmetic (Blackwell) -------------------------------------------------------
+// sm_100 has two-wide FP32 instructions (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2)
+// whose operands take per-half swap and negate modifiers for free.  A complex<f32> add is therefore ONE
+// instruction and a complex multiply TWO (FMUL2 + FFMA2), half of the scalar sequence.  The FFT kernels
+// are bound by instruction issue and the LSU pipe, not by the FP32 pipe (ncu, profiles/r1a_*), so halving
+// the FP instruction count is the largest single lever.  Rounding is identical to the scalar forms
+// (IEEE round-to-nearest per component; cmul = fma(-a.y, w.y, a.x*w.x), the same contraction nvcc makes).
+#if defined(__CUDA_ARCH__) && !defined(B2_NO_F32X2)
+#define B2_F32X2 1
+B2_D unsigned long long pk2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+B2_D cx<float> upk2(unsigned long long v) {
+    cx<float> r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+B2_D unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+B2_D unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+B2_D unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+B2_D unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+#endif
+
+template <typename T> B2_HD cx<T> operator+(cx<T> a, cx<T> b) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)));
+#endif
+    return mk<T>(a.x + b.x, a.y + b.y);
+}
+template <typename T> B2_HD cx<T> operator-(cx<T> a, cx<T> b) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(sub2(pk2(a.x, a.y), pk2(b.x, b.y)));
+#endif
+    return mk<T>(a.x - b.x, a.y - b.y);
+}
+// (a.x + i a.y)(w.x + i w.y)
 template <typename T> B2_HD cx<T> cmul(cx<T> a, cx<T> w) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4)
+        return upk2(fma2(pk2(-a.y, a.x), pk2(w.y, w.y), mul2(pk2(a.x, a.y), pk2(w.x, w.x))));
+#endif
     return mk<T>(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
 }
 // a * conj(w)
 template <typename T> B2_HD cx<T> cmulc(cx<T> a, cx<T> w) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4)
+        return upk2(fma2(pk2(a.y, -a.x), pk2(w.y, w.y), mul2(pk2(a.x, a.y), pk2(w.x, w.x))));
+#endif
     return mk<T>(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+// a * s (real scalar)
+template <typename T> B2_HD cx<T> scale(cx<T> a, T s) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(mul2(pk2(a.x, a.y), pk2(s, s)));
+#endif
+    return mk<T>(a.x * s, a.y * s);
+}
+// a + s * b, s real
+template <typename T> B2_HD cx<T> axpy(cx<T> a, T s, cx<T> b) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(fma2(pk2(b.x, b.y), pk2(s, s), pk2(a.x, a.y)));
+#endif
+    return mk<T>(a.x + s * b.x, a.y + s * b.y);
 }
 template <typename T> B2_HD cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
 // multiply by -i  (forward quarter turn, twiddle(1,4))
 template <typename T> B2_HD cx<T> mul_mi(cx<T> a) { return mk<T>(a.y, -a.x); }
+// a + (-i) b   and   a - (-i) b : the quarter turn rides on the add's operand modifiers
+template <typename T> B2_HD cx<T> add_mi(cx<T> a, cx<T> b) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(add2(pk2(a.x, a.y), pk2(b.y, -b.x)));
+#endif
+    return mk<T>(a.x + b.y, a.y - b.x);
+}
+template <typename T> B2_HD cx<T> sub_mi(cx<T> a, cx<T> b) {
+#if defined(B2_F32X2)
+    if constexpr (sizeof(T) == 4) return upk2(add2(pk2(a.x, a.y), pk2(-b.y, b.x)));
+#endif
+    return mk<T>(a.x - b.y, a.y + b.x);
+}
 // swap re <-> im.  ifft(x) = swap(fft(swap(x))): the whole inverse direction is a register
 // renaming at the outermost load and store of a plan, every table stays "forward".
 template <typename T> B2_HD cx<T> swap_ri(cx<T> a) { return mk<T>(a.y, a.x); }
@@ -122,6 +209,12 @@ struct Radices {
         return off;
     }
     static constexpr int tw_total() { return tw_offset(N); }
+    static constexpr bool all_pow2() {
+        constexpr int a[] = {Rs...};
+        for (int i = 0; i < N; ++i)
+            if (a[i] & (a[i] - 1)) return false;
+        return true;
+    }
 };
 
 template <int A, int B> struct StaticMax { static constexpr int v = A > B ? A : B; };

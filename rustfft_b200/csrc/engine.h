@@ -42,6 +42,7 @@ struct Geo {
     static constexpr int LP = (F <= 1) ? LPAD : (F >= UNIT ? LPR + 1 : LPR + UNIT / F);
     static constexpr int SMEM_ELEMS = (NS > 1) ? F * LP : 0;
     static constexpr int TW_ELEMS = RL::tw_total();
+    static constexpr bool POW2 = RL::all_pow2() && ((TP & (TP - 1)) == 0);
     static B2_HD int sidx(int f, int e) { return f * LP + e + (PS ? (e >> PS) : 0); }
     static_assert(RL::product() == L, "radices must multiply to L");
     static_assert(L % E == 0, "E must divide L");
@@ -91,8 +92,16 @@ struct Engine {
                 for (int m = 0; m < R; ++m) out[u + m * Q] = a[m];
             } else {
                 const int base = (i - k) * R + k;
-                B2_UNROLL
-                for (int m = 0; m < R; ++m) smem[G::sidx(f, base + m * p)] = a[m];
+                if constexpr (G::POW2) {
+                    // pad(base + m p) == pad(base) + pad(m p) for power-of-two radices (k + m p never carries
+                    // into bit 4 beyond what m p alone does): one address, compile-time offsets
+                    cx<T>* wp = smem + G::sidx(f, base);
+                    B2_UNROLL
+                    for (int m = 0; m < R; ++m) wp[m * p + (G::PS ? ((m * p) >> G::PS) : 0)] = a[m];
+                } else {
+                    B2_UNROLL
+                    for (int m = 0; m < R; ++m) smem[G::sidx(f, base + m * p)] = a[m];
+                }
             }
         }
         if (last) {
@@ -103,8 +112,15 @@ struct Engine {
 
     template <int S>
     static B2_HD void read(int f, int j, cx<T> (&v)[E], const cx<T>* smem) {
-        B2_UNROLL
-        for (int q = 0; q < E; ++q) v[q] = smem[G::sidx(f, j + G::TP * q)];
+        if constexpr (G::POW2) {
+            // pad(j + TP q) == pad(j) + pad(TP q) when TP is a power of two: one address, constant offsets
+            const cx<T>* rp = smem + G::sidx(f, j);
+            B2_UNROLL
+            for (int q = 0; q < E; ++q) v[q] = rp[G::TP * q + (G::PS ? ((G::TP * q) >> G::PS) : 0)];
+        } else {
+            B2_UNROLL
+            for (int q = 0; q < E; ++q) v[q] = smem[G::sidx(f, j + G::TP * q)];
+        }
     }
 
     // Phase numbering of one FFT:  0 = stage 0;  2s-1 = read inputs of stage s;  2s = stage s.

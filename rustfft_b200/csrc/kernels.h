@@ -233,8 +233,11 @@ struct FftKernel {
         if constexpr (P == 0) {
             int f, j;
             Eng::template owner<0>(tid, f, j);
-            const uint64_t g = (uint64_t)bid * G::F + f;
-            const auto st = p.load.prep(g, g < p.n_fft);
+            // FFTs past the end of the launch (last CTA of a ragged batch) re-read the last valid FFT
+            // instead of predicating every load; their stores are masked below
+            uint64_t g = (uint64_t)bid * G::F + f;
+            if (g >= p.n_fft) g = p.n_fft - 1;
+            const auto st = p.load.prep(g, true);
             B2_UNROLL
             for (int q = 0; q < G::E; ++q) r.v[q] = p.load.get(st, j + G::TP * q);
         }
