@@ -116,6 +116,36 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
     return check(cudaGetLastError(), "kernel launch");
 }
 
+// persistent pipelined kernels: grid = SMs x resident CTAs (queried once per kernel and device)
+template <class KT>
+static bool launch_pipelined(const typename KT::Params& p, stream_t s) {
+    if (p.n_items == 0) return true;
+    static std::atomic<int> grid_for_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int grid = grid_for_dev[dev & 63].load(std::memory_order_acquire);
+    if (grid == 0) {
+        if (!check(cudaFuncSetAttribute(run_pipelined<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return false;
+        cudaFuncSetAttribute(run_pipelined<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int per_sm = 0, sms = 0;
+        if (!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_pipelined<KT>, KT::NT, KT::SMEM_BYTES),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+            return false;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1 || sms < 1) {
+            g_err = "pipelined kernel does not fit on an SM";
+            return false;
+        }
+        grid = per_sm * sms;
+        grid_for_dev[dev & 63].store(grid, std::memory_order_release);
+    }
+    const unsigned g = (unsigned)((uint64_t)grid < (uint64_t)p.n_items ? grid : (int)p.n_items);
+    run_pipelined<KT><<<g, KT::NT, KT::SMEM_BYTES, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
 }  // namespace rt
 }  // namespace b2
 

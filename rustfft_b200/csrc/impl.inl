@@ -84,6 +84,7 @@ B2_TILE(double, 1024, 8, 4, 2, 8, 8, 8)
 
 // largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
 template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
+static constexpr size_t MAX_SMEM_PER_CTA = 227 * 1024;  // opt-in dynamic shared memory limit of sm_100
 static constexpr uint32_t FUSED_CONV_MAX = 4096;  // largest inner FFT of the fused Bluestein / Rader kernels
 static constexpr uint32_t TILE_MIN = 64, TILE_MAX = 1024;
 
@@ -151,6 +152,15 @@ static uint64_t chunk_bytes() {
     return v;
 }
 
+// B200FFT_PIPELINE=0 selects the plain (non-persistent, LDG-based) kernels -- kept for A/B measurements
+static bool use_pipelined() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_PIPELINE");
+        return !(e && std::atoi(e) == 0);
+    }();
+    return v;
+}
+
 static bool tile1024_wide() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_TILE1024");
@@ -174,6 +184,20 @@ struct Builder {
             if (!tw) return false;
         }
         pl.exec = [tw](const ExecCtx& c) {
+            if constexpr (G::NS >= 2 && 2 * G::F * G::LP * sizeof(C) + 2048 <= MAX_SMEM_PER_CTA) {
+                // persistent TMA-pipelined kernel whenever the caller's buffer allows 16-byte bulk copies
+                if (use_pipelined() && (reinterpret_cast<uintptr_t>(c.in) & 15u) == 0) {
+                    using KP = PipeKernel<G, JF, XformSwap<T, SW>, StoreRows<T, SW>>;
+                    typename KP::Params q;
+                    q.in = (const C*)c.in;
+                    q.xform = XformSwap<T, SW>{};
+                    q.store = StoreRows<T, SW>{(C*)c.out, (uint32_t)L};
+                    q.tw = tw;
+                    q.n_fft = c.batch;
+                    q.n_items = (uint32_t)((c.batch + G::F - 1) / G::F);
+                    return rt::launch_pipelined<KP>(q, c.stream);
+                }
+            }
             typename KT::Params p;
             p.load = LoadRows<T, SW>{(const C*)c.in, (uint32_t)L};
             p.store = StoreRows<T, SW>{(C*)c.out, (uint32_t)L};
@@ -241,6 +265,17 @@ struct Builder {
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         fns.b = [=](const C* work, C* out, uint64_t nb, rt::stream_t s) {
+            if (use_pipelined() && (reinterpret_cast<uintptr_t>(work) & 15u) == 0) {
+                using KP = PipeKernel<G, FF, XformRowTw<T>, StoreTransposed<T, SW>>;
+                typename KP::Params q;
+                q.in = work;
+                q.xform = XformRowTw<T>{full_tw, (uint32_t)G::L, lg1};
+                q.store = StoreTransposed<T, SW>{out, lgN, lg1};
+                q.tw = tw;
+                q.n_fft = nb << lg1;
+                q.n_items = (uint32_t)((q.n_fft + G::F - 1) / G::F);
+                return rt::launch_pipelined<KP>(q, s);
+            }
             typename KT::Params p;
             p.load = LoadRowsTw<T>{work, full_tw, (uint32_t)G::L, lg1};
             p.store = StoreTransposed<T, SW>{out, lgN, lg1};

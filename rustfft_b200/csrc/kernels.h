@@ -20,6 +20,7 @@
 // outermost store (ifft(x) = swap(fft(swap(x))), swap = exchange re/im) -- see common.h.
 #pragma once
 #include "engine.h"
+#include "tma.h"
 
 namespace b2 {
 
@@ -411,6 +412,88 @@ struct RaderKernel {
 };
 
 // ------------------------------------------------------------------------------------------
+// Persistent, software-pipelined one-pass kernels (contiguous tiles).
+//
+// A tile = F whole FFTs that are contiguous in global memory (Direct: F transforms; four-step pass B:
+// F rows of the [k1][n2] intermediate).  CTAs are persistent (grid = SMs x resident CTAs) and stride
+// over the tiles; while tile i is transformed out of shared-memory buffer i&1, ONE thread has already
+// queued tile i+1 into the other buffer with a single TMA bulk copy (cp.async.bulk -> UBLKCP) that
+// completes on an mbarrier.  The signal therefore never passes through the LSU's global-load queue
+// (round-1 ncu: lg_throttle / mio_throttle were the top stalls of the LDG-based kernels) and the copy
+// of the next tile overlaps all of the current tile's butterflies.  The buffer that received the
+// dense tile is then reused, in place, as the padded exchange buffer of the stages.
+//   phase 0     : dense tile -> registers  (+ Xform: re/im swap, or the inter-pass twiddle table)
+//   phase 1..   : the engine's phases
+//   last phase  : Store functor straight from registers (coalesced)
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SWAP>
+struct XformSwap {  // Direct plans: optional re<->im swap of an inverse plan
+    struct St {};
+    B2_HD St prep(uint64_t) const { return St{}; }
+    B2_HD cx<T> apply(const St&, int, cx<T> v) const { return SWAP ? swap_ri(v) : v; }
+};
+template <typename T>
+struct XformRowTw {  // four-step pass B: times W_N^(k1*n2), table [k1][n2]
+    const cx<T>* tw;
+    uint32_t len, lg1;
+    struct St { const cx<T>* t; };
+    B2_HD St prep(uint64_t g) const { return St{tw + (g & ((1ull << lg1) - 1)) * (uint64_t)len}; }
+    B2_HD cx<T> apply(const St& s, int e, cx<T> v) const { return cmul(v, ldg(s.t + e)); }
+};
+
+template <class G, Map M1, class Xform, class Store>
+struct PipeKernel {
+    using T = typename G::T;
+    using Eng = Engine<G, JF, M1>;
+    static constexpr int NT = G::NT;
+    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT);
+    static constexpr int NPHASE = Eng::NPHASE + 1;
+    static constexpr size_t BUF_ELEMS = ((size_t)G::F * G::LP + 15) / 16 * 16;  // >= F*L, 128-byte multiple
+    static constexpr size_t BUF_BYTES = BUF_ELEMS * sizeof(cx<T>);
+    static constexpr size_t SMEM_BYTES = 2 * BUF_BYTES + 16;  // two buffers + two mbarriers
+    static_assert(G::NS >= 2, "single-stage sizes use the plain kernels");
+    struct Params {
+        const cx<T>* in;   // tiles are contiguous: tile i starts at in + i*F*L
+        Xform xform;
+        Store store;
+        const cx<T>* tw;
+        uint64_t n_fft;
+        uint32_t n_items;
+    };
+    struct Regs { cx<T> v[G::E]; };
+
+    static B2_HD const cx<T>* fetch_src(const Params& p, uint32_t item) { return p.in + (uint64_t)item * G::F * G::L; }
+    static B2_HD uint32_t fetch_bytes(const Params& p, uint32_t item) {
+        const uint64_t first = (uint64_t)item * G::F;
+        const uint64_t valid = (p.n_fft - first < (uint64_t)G::F) ? (p.n_fft - first) : (uint64_t)G::F;
+        return (uint32_t)(valid * G::L * sizeof(cx<T>));
+    }
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t item, int tid, Regs& r, cx<T>* buf) {
+        if constexpr (P == 0) {
+            int f, j;
+            tid_to_fj<G, JF>(tid, f, j);
+            uint64_t g = (uint64_t)item * G::F + f;
+            const auto st = p.xform.prep(g < p.n_fft ? g : p.n_fft - 1);
+            const cx<T>* src = buf + f * G::L + j;
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) r.v[q] = p.xform.apply(st, j + G::TP * q, src[G::TP * q]);
+        } else {
+            Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
+        }
+        if constexpr (P == NPHASE - 1) {
+            int f, j;
+            Eng::out_owner(tid, f, j);
+            const uint64_t g = (uint64_t)item * G::F + f;
+            const auto st = p.store.prep(g, g < p.n_fft);
+            B2_UNROLL
+            for (int q = 0; q < G::E; ++q) p.store.put(st, j + G::TP * q, r.v[q]);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Device entry point shared by all kernels.
 // ------------------------------------------------------------------------------------------
 template <class KT, int P>
@@ -434,6 +517,43 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel(const __gri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));
+}
+
+template <class KT>
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_pipelined(const __grid_constant__ typename KT::Params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using T = typename KT::T;
+    cx<T>* buf0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* buf1 = reinterpret_cast<cx<T>*>(smem_raw + KT::BUF_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * KT::BUF_BYTES);
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&bar[0], 1);
+        tma::mbar_init(&bar[1], 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t item = blockIdx.x;
+    if (tid == 0 && item < p.n_items) {
+        const uint32_t bytes = KT::fetch_bytes(p, item);
+        tma::mbar_arrive_expect_tx(&bar[0], bytes);
+        tma::bulk_g2s(buf0, KT::fetch_src(p, item), bytes, &bar[0]);
+    }
+    for (uint32_t it = 0; item < p.n_items; item += gridDim.x, ++it) {
+        const uint32_t cur = it & 1u;
+        cx<T>* buf = cur ? buf1 : buf0;
+        const uint32_t next = item + gridDim.x;
+        if (tid == 0 && next < p.n_items) {
+            // the other buffer was last touched (generic proxy) before the final barrier of the previous tile
+            tma::fence_proxy_async();
+            const uint32_t bytes = KT::fetch_bytes(p, next);
+            tma::mbar_arrive_expect_tx(&bar[cur ^ 1u], bytes);
+            tma::bulk_g2s(cur ? buf0 : buf1, KT::fetch_src(p, next), bytes, &bar[cur ^ 1u]);
+        }
+        tma::mbar_wait(&bar[cur], (it >> 1) & 1u);
+        typename KT::Regs r;
+        PhaseRunner<KT, 0>::run(p, item, tid, r, buf);
+    }
 }
 #endif
 
