@@ -12,6 +12,10 @@ template <typename T> struct K {
     static constexpr T rsqrt2 = (T)0.70710678118654752440084436210484903928L;
     static constexpr T c16_1 = (T)0.92387953251128675612818318939678828682L;  // cos(pi/8)
     static constexpr T s16_1 = (T)0.38268343236508977172845998403039886676L;  // sin(pi/8)
+    static constexpr T c32_1 = (T)0.98078528040323044912618223613423903697L;  // cos(pi/16)
+    static constexpr T s32_1 = (T)0.19509032201612826784828486847702224093L;  // sin(pi/16)
+    static constexpr T c32_3 = (T)0.83146961230254523707878837761790575673L;  // cos(3pi/16)
+    static constexpr T s32_3 = (T)0.55557023301960222474283081394853287438L;  // sin(3pi/16)
     // radix 3
     static constexpr T c3 = (T)-0.5L;
     static constexpr T s3 = (T)0.86602540378443864676372317075293618347L;  // sin(2pi/3)
@@ -139,6 +143,59 @@ template <typename T> B2_HD void bf16(cx<T> (&v)[16]) {
     }
 }
 
+// multiply by W32^m = exp(-2 pi i m / 32), m compile-time (0..31): trivial rotations and the eighth
+// roots use the modifier forms, the rest one complex multiply with a literal constant
+template <int M, typename T> B2_HD cx<T> mul_w32(cx<T> a) {
+    constexpr int m = M & 31;
+    if constexpr (m == 0) return a;
+    else if constexpr (m == 8) return mul_mi(a);
+    else if constexpr (m == 16) return mk<T>(-a.x, -a.y);
+    else if constexpr (m == 24) return mk<T>(-a.y, a.x);
+    else if constexpr (m == 4) return mul_w8_1(a);
+    else if constexpr (m == 12) return mul_w8_3(a);
+    else if constexpr (m == 20) return scale(add_mi(a, a), -K<T>::rsqrt2);
+    else if constexpr (m == 28) return scale(sub_mi(a, a), K<T>::rsqrt2);
+    else {
+        // cos/sin(2 pi m / 32) from the first-octant constants
+        constexpr int o = m & 7;  // position inside the octant pair
+        constexpr int q = m >> 3; // quadrant
+        // angle = q*90deg + o*11.25deg ; cos/sin of o*11.25: o=1 (c32_1,s32_1) 2 (c16_1,s16_1) 3 (c32_3,s32_3)
+        // 5 -> (s32_3,c32_3) 6 -> (s16_1,c16_1) 7 -> (s32_1,c32_1)
+        constexpr T c0 = (o == 1) ? K<T>::c32_1 : (o == 2) ? K<T>::c16_1 : (o == 3) ? K<T>::c32_3
+                       : (o == 5) ? K<T>::s32_3 : (o == 6) ? K<T>::s16_1 : K<T>::s32_1;
+        constexpr T s0 = (o == 1) ? K<T>::s32_1 : (o == 2) ? K<T>::s16_1 : (o == 3) ? K<T>::s32_3
+                       : (o == 5) ? K<T>::c32_3 : (o == 6) ? K<T>::c16_1 : K<T>::c32_1;
+        // rotate by quadrant: exp(-i(theta0 + q pi/2)) -> (cos, -sin)
+        constexpr T c = (q == 0) ? c0 : (q == 1) ? -s0 : (q == 2) ? -c0 : s0;
+        constexpr T sn = (q == 0) ? s0 : (q == 1) ? c0 : (q == 2) ? -s0 : -c0;
+        return cmul(a, mk<T>(c, -sn));
+    }
+}
+
+// radix 32 = 4 x 8:  n = 8*n1 + n2, k = k1 + 4*k2.  4-point over n1 for each n2, twiddle W32^(n2*k1),
+// 8-point over n2 for each k1.
+template <typename T> B2_HD void bf32(cx<T> (&v)[32]) {
+    B2_UNROLL
+    for (int n2 = 0; n2 < 8; ++n2) bf4(v[n2], v[8 + n2], v[16 + n2], v[24 + n2]);  // -> v[8*k1 + n2]
+#define B2_TW32(k1, n2) v[8 * k1 + n2] = mul_w32<k1 * n2>(v[8 * k1 + n2]);
+    B2_TW32(1, 1) B2_TW32(1, 2) B2_TW32(1, 3) B2_TW32(1, 4) B2_TW32(1, 5) B2_TW32(1, 6) B2_TW32(1, 7)
+    B2_TW32(2, 1) B2_TW32(2, 2) B2_TW32(2, 3) B2_TW32(2, 4) B2_TW32(2, 5) B2_TW32(2, 6) B2_TW32(2, 7)
+    B2_TW32(3, 1) B2_TW32(3, 2) B2_TW32(3, 3) B2_TW32(3, 4) B2_TW32(3, 5) B2_TW32(3, 6) B2_TW32(3, 7)
+#undef B2_TW32
+    cx<T> o[32];
+    B2_UNROLL
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cx<T> t[8];
+        B2_UNROLL
+        for (int n2 = 0; n2 < 8; ++n2) t[n2] = v[8 * k1 + n2];
+        bf8(t);  // -> k2
+        B2_UNROLL
+        for (int k2 = 0; k2 < 8; ++k2) o[k1 + 4 * k2] = t[k2];
+    }
+    B2_UNROLL
+    for (int i = 0; i < 32; ++i) v[i] = o[i];
+}
+
 // dispatch on a register array
 template <int R, typename T> struct Bfly;
 template <typename T> struct Bfly<1, T> { static B2_HD void run(cx<T> (&)[1]) {} };
@@ -151,5 +208,6 @@ template <typename T> struct Bfly<7, T> {
 };
 template <typename T> struct Bfly<8, T> { static B2_HD void run(cx<T> (&v)[8]) { bf8(v); } };
 template <typename T> struct Bfly<16, T> { static B2_HD void run(cx<T> (&v)[16]) { bf16(v); } };
+template <typename T> struct Bfly<32, T> { static B2_HD void run(cx<T> (&v)[32]) { bf32(v); } };
 
 }  // namespace b2

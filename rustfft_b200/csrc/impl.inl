@@ -31,13 +31,18 @@ static int fail(int code, const std::string& msg) {
 }
 
 // ---- geometry registry ---------------------------------------------------------------------
-template <typename T, int L> struct DirectGeo;  // whole transform per CTA pass, threads: j fastest
-template <typename T, int L> struct TileGeo;    // four-step tiles: F FFTs side by side
+// V = tuning variant: 0 = radix <= 16 stages (16 elements per thread), 1 = radix-32 stages (32 per thread)
+template <typename T, int L, int V = 0> struct DirectGeo;  // whole transform per CTA pass, threads: j fastest
+template <typename T, int L, int V = 0> struct TileGeo;    // four-step tiles: F FFTs side by side
 
 #define B2_DIRECT(T, L, E, F, ...) \
-    template <> struct DirectGeo<T, L> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+    template <> struct DirectGeo<T, L, 0> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
 #define B2_TILE(T, L, E, F, ...) \
-    template <> struct TileGeo<T, L> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+    template <> struct TileGeo<T, L, 0> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+#define B2_DIRECT_V1(T, L, E, F, ...) \
+    template <> struct DirectGeo<T, L, 1> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+#define B2_TILE_V1(T, L, E, F, ...) \
+    template <> struct TileGeo<T, L, 1> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
 
 B2_DIRECT(float, 2, 2, 128, 2)
 B2_DIRECT(float, 4, 4, 128, 4)
@@ -73,8 +78,13 @@ B2_TILE(float, 128, 16, 16, 8, 16)
 B2_TILE(float, 256, 16, 16, 16, 16)
 B2_TILE(float, 512, 16, 16, 2, 16, 16)
 B2_TILE(float, 1024, 16, 8, 16, 16, 4)
-// tuning variant (B200FFT_TILE1024=16): 16-wide 1024-point tiles, one 1024-thread CTA per SM
-template <> struct TileGeo<float, 1025> { using type = Geo<float, 1024, 16, 16, Radices<4, 16, 16>>; };
+// radix-32 variants (f32): every four-step pass becomes two stages = one shared-memory exchange
+B2_TILE_V1(float, 512, 32, 16, 16, 32)
+B2_TILE_V1(float, 1024, 32, 8, 32, 32)
+B2_DIRECT_V1(float, 512, 32, 16, 16, 32)
+B2_DIRECT_V1(float, 1024, 32, 8, 32, 32)
+B2_DIRECT_V1(float, 8192, 32, 1, 16, 16, 32)
+B2_DIRECT_V1(float, 16384, 32, 1, 16, 32, 32)
 
 B2_TILE(double, 64, 8, 16, 8, 8)
 B2_TILE(double, 128, 8, 16, 2, 8, 8)
@@ -152,31 +162,40 @@ static uint64_t chunk_bytes() {
     return v;
 }
 
-// B200FFT_PIPELINE=0 selects the plain (non-persistent, LDG-based) kernels -- kept for A/B measurements
+// B200FFT_PIPELINE=1 selects the persistent TMA-pipelined kernels (cp.async.bulk + mbarrier double
+// buffering).  Measured in round 1 (profiles/r1e_*): correct, but 10-13 % slower than the plain kernels --
+// the second tile buffer halves the resident CTAs of the 70 KiB tiles and the dense tile costs one more
+// shared-memory pass -- so they stay opt-in until that is fixed.
 static bool use_pipelined() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_PIPELINE");
-        return !(e && std::atoi(e) == 0);
+        return e && std::atoi(e) == 1;
     }();
     return v;
 }
 
-static bool tile1024_wide() {
+// B200FFT_RADIX32=0 disables the radix-32 geometries (A/B measurements)
+static bool use_radix32() {
     static bool v = [] {
-        const char* e = std::getenv("B200FFT_TILE1024");
-        return e && std::atoi(e) == 16;
+        const char* e = std::getenv("B200FFT_RADIX32");
+        return !(e && std::atoi(e) == 0);
     }();
     return v;
 }
+template <typename T, int L> struct HasV1 { static constexpr bool direct = false, tile = false; };
+template <> struct HasV1<float, 512> { static constexpr bool direct = true, tile = true; };
+template <> struct HasV1<float, 1024> { static constexpr bool direct = true, tile = true; };
+template <> struct HasV1<float, 8192> { static constexpr bool direct = true, tile = false; };
+template <> struct HasV1<float, 16384> { static constexpr bool direct = true, tile = false; };
 
 template <typename T>
 struct Builder {
     typedef cx<T> C;
 
     // ---------------- Direct ----------------
-    template <int L, bool SW>
+    template <int L, bool SW, int V = 0>
     static bool make_direct_t(b200fft_plan& pl) {
-        using G = typename DirectGeo<T, L>::type;
+        using G = typename DirectGeo<T, L, V>::type;
         using KT = FftKernel<G, JF, JF, LoadRows<T, SW>, StoreRows<T, SW>>;
         const C* tw = nullptr;
         if (G::TW_ELEMS) {
@@ -211,6 +230,9 @@ struct Builder {
     }
     template <int L>
     static bool make_direct(b200fft_plan& pl) {
+        if constexpr (HasV1<T, L>::direct) {
+            if (use_radix32()) return pl.direction ? make_direct_t<L, true, 1>(pl) : make_direct_t<L, false, 1>(pl);
+        }
         return pl.direction ? make_direct_t<L, true>(pl) : make_direct_t<L, false>(pl);
     }
     static bool make_direct_rt(b200fft_plan& pl, uint32_t L) {
@@ -242,9 +264,12 @@ struct Builder {
         std::function<bool(const C* in, C* work, uint64_t nb, rt::stream_t)> a;
         std::function<bool(const C* work, C* out, uint64_t nb, rt::stream_t)> b;
     };
-    template <int L1, bool SW>
+    template <int L1, bool SW, int V = 0>
     static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, PassFns& fns) {
-        using G = typename TileGeo<T, L1>::type;
+        if constexpr (V == 0 && HasV1<T, L1>::tile) {
+            if (use_radix32()) return make_pass_a<L1, SW, 1>(pl, lgN, lg2, fns);
+        }
+        using G = typename TileGeo<T, L1, V>::type;
         using KT = FftKernel<G, FF, FF, LoadCols<T, SW>, StoreCols<T>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
@@ -258,9 +283,12 @@ struct Builder {
         };
         return true;
     }
-    template <int L2, bool SW>
+    template <int L2, bool SW, int V = 0>
     static bool make_pass_b(b200fft_plan& pl, uint32_t lgN, uint32_t lg1, const C* full_tw, PassFns& fns) {
-        using G = typename TileGeo<T, L2>::type;
+        if constexpr (V == 0 && HasV1<T, L2>::tile) {
+            if (use_radix32()) return make_pass_b<L2, SW, 1>(pl, lgN, lg1, full_tw, fns);
+        }
+        using G = typename TileGeo<T, L2, V>::type;
         using KT = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposed<T, SW>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
@@ -292,11 +320,7 @@ struct Builder {
             case 128: return make_pass_a<128, SW>(pl, lgN, lg2, f);
             case 256: return make_pass_a<256, SW>(pl, lgN, lg2, f);
             case 512: return make_pass_a<512, SW>(pl, lgN, lg2, f);
-            case 1024:
-                if constexpr (sizeof(T) == 4) {
-                    if (tile1024_wide()) return make_pass_a<1025, SW>(pl, lgN, lg2, f);
-                }
-                return make_pass_a<1024, SW>(pl, lgN, lg2, f);
+            case 1024: return make_pass_a<1024, SW>(pl, lgN, lg2, f);
         }
         return false;
     }
@@ -307,11 +331,7 @@ struct Builder {
             case 128: return make_pass_b<128, SW>(pl, lgN, lg1, tw, f);
             case 256: return make_pass_b<256, SW>(pl, lgN, lg1, tw, f);
             case 512: return make_pass_b<512, SW>(pl, lgN, lg1, tw, f);
-            case 1024:
-                if constexpr (sizeof(T) == 4) {
-                    if (tile1024_wide()) return make_pass_b<1025, SW>(pl, lgN, lg1, tw, f);
-                }
-                return make_pass_b<1024, SW>(pl, lgN, lg1, tw, f);
+            case 1024: return make_pass_b<1024, SW>(pl, lgN, lg1, tw, f);
         }
         return false;
     }
@@ -372,9 +392,12 @@ struct Builder {
         std::function<bool(const C* w1, C* w2, const C* in, C* out, uint64_t nb, rt::stream_t)> b1;
         std::function<bool(const C* w2, C* out, uint64_t nb, rt::stream_t)> b2;
     };
-    template <int L1, bool SW>
+    template <int L1, bool SW, int V = 0>
     static bool make_conv_a1(b200fft_plan& pl, const ConvTables& t, ConvFns& f) {
-        using G = typename TileGeo<T, L1>::type;
+        if constexpr (V == 0 && HasV1<T, L1>::tile) {
+            if (use_radix32()) return make_conv_a1<L1, SW, 1>(pl, t, f);
+        }
+        using G = typename TileGeo<T, L1, V>::type;
         using KT = FftKernel<G, FF, FF, LoadColsConv<T, SW>, StoreCols<T>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
@@ -388,15 +411,18 @@ struct Builder {
         };
         return true;
     }
-    template <int L2, bool SW>
+    template <int L2, bool SW, int V = 0>
     static bool make_conv_b(b200fft_plan& pl, const ConvTables& t, ConvFns& f) {
-        using G = typename TileGeo<T, L2>::type;
+        if constexpr (V == 0 && HasV1<T, L2>::tile) {
+            if (use_radix32()) return make_conv_b<L2, SW, 1>(pl, t, f);
+        }
+        using G = typename TileGeo<T, L2, V>::type;
         using K0 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 0>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
         f.b1 = [=](const C* w1, C* w2, const C* in, C* out, uint64_t nb, rt::stream_t s) {
             typename K0::Params p;
-            p.load = LoadRowsTw<T>{w1, t.full_tw, (uint32_t)L2, t.lg1};
+            p.load = LoadRowsTw<T>{w1, t.full_tw, (uint32_t)G::L, t.lg1};
             p.store = StoreTransposedConv<T, SW, 0>{w2, t.mult, nullptr, nullptr, t.rader ? in : nullptr, out, t.n, t.lgM, t.lg1};
             p.tw = tw;
             p.n_fft = nb << t.lg1;
@@ -406,7 +432,7 @@ struct Builder {
             using K1 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 1>>;
             f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
                 typename K1::Params p;
-                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)L2, t.lg1};
+                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)G::L, t.lg1};
                 p.store = StoreTransposedConv<T, SW, 1>{out, nullptr, t.scatter, nullptr, nullptr, nullptr, t.n, t.lgM, t.lg1};
                 p.tw = tw;
                 p.n_fft = nb << t.lg1;
@@ -416,7 +442,7 @@ struct Builder {
             using K2 = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposedConv<T, SW, 2>>;
             f.b2 = [=](const C* w2, C* out, uint64_t nb, rt::stream_t s) {
                 typename K2::Params p;
-                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)L2, t.lg1};
+                p.load = LoadRowsTw<T>{w2, t.full_tw, (uint32_t)G::L, t.lg1};
                 p.store = StoreTransposedConv<T, SW, 2>{out, nullptr, nullptr, t.chirp, nullptr, nullptr, t.n, t.lgM, t.lg1};
                 p.tw = tw;
                 p.n_fft = nb << t.lg1;

@@ -24,7 +24,13 @@
 
 namespace b2 {
 
-constexpr int default_min_blocks(int nt) { return nt >= 1024 ? 1 : (nt >= 512 ? 2 : (nt >= 256 ? 3 : 4)); }
+// resident CTAs per SM the register allocator must leave room for: 64 registers per thread for the
+// 16-element geometries (2048 threads per SM), 128 for the 32-element (radix-32) ones
+constexpr int default_min_blocks(int nt, int e = 16) {
+    const int target_threads = e >= 32 ? 512 : 1024;
+    const int b = target_threads / nt;
+    return b < 1 ? 1 : (b > 8 ? 8 : b);
+}
 
 // ------------------------------------------------------------------------------------------
 // Functors.  prep(g, ok) is evaluated once per thread (g = global FFT index of this thread's
@@ -218,7 +224,7 @@ struct FftKernel {
     using T = typename G::T;
     using Eng = Engine<G, M0, M1>;
     static constexpr int NT = G::NT;
-    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT);
+    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT, G::E);
     static constexpr int NPHASE = Eng::NPHASE;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)G::SMEM_ELEMS;
     struct Params {
@@ -446,7 +452,7 @@ struct PipeKernel {
     using T = typename G::T;
     using Eng = Engine<G, JF, M1>;
     static constexpr int NT = G::NT;
-    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT);
+    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT, G::E);
     static constexpr int NPHASE = Eng::NPHASE + 1;
     static constexpr size_t BUF_ELEMS = ((size_t)G::F * G::LP + 15) / 16 * 16;  // >= F*L, 128-byte multiple
     static constexpr size_t BUF_BYTES = BUF_ELEMS * sizeof(cx<T>);
