@@ -75,6 +75,53 @@ static bool stream_sync(stream_t s) { return check(cudaStreamSynchronize(s), "cu
 namespace b2 {
 namespace rt {
 
+// once per (kernel, device): opt in to > 48 KiB dynamic shared memory, and ask for a shared-memory
+// carveout that fits as many CTAs as registers and threads allow (the driver's default carveout left
+// the 70 KiB tile kernels at 1 CTA/SM in the first round-1 capture)
+template <class KT>
+static bool ensure_configured() {
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (configured.load(std::memory_order_acquire) & bit) return true;
+    if (KT::SMEM_BYTES > 48 * 1024 &&
+        !check(cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+               "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+        return false;
+    if (KT::SMEM_BYTES > 0) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, run_kernel<KT>) == cudaSuccess) {
+            const int regs = ((fa.numRegs + 7) / 8) * 8;
+            int want = 65536 / (regs * KT::NT);
+            if (want > 2048 / KT::NT) want = 2048 / KT::NT;
+            if (want < 1) want = 1;
+            const size_t need = (size_t)want * (KT::SMEM_BYTES + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        cudaGetLastError();
+    }
+    configured.fetch_or(bit, std::memory_order_release);
+    return true;
+}
+
+// CTAs of this kernel the whole device holds at once (one "wave"); the planner sizes the L2 chunks of
+// multi-pass plans so that every launch is close to a whole number of waves
+template <class KT>
+static int resident_ctas() {
+    if (!ensure_configured<KT>()) return 0;
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_kernel<KT>, KT::NT, KT::SMEM_BYTES) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return per_sm * sms;
+}
+
 template <class KT>
 static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
     if (ctas == 0) return true;
@@ -82,36 +129,7 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
         g_err = "grid too large";
         return false;
     }
-    // once per (kernel, device): opt in to > 48 KiB dynamic shared memory, and ask for a shared-memory
-    // carveout that fits as many CTAs as registers and threads allow (the driver's default carveout left
-    // the 70 KiB tile kernels at 1 CTA/SM in the first round-1 capture)
-    static std::atomic<uint64_t> configured{0};
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const uint64_t bit = 1ull << (dev & 63);
-        if (!(configured.load(std::memory_order_acquire) & bit)) {
-            if (KT::SMEM_BYTES > 48 * 1024 &&
-                !check(cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
-                       "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
-                return false;
-            if (KT::SMEM_BYTES > 0) {
-                cudaFuncAttributes fa;
-                if (cudaFuncGetAttributes(&fa, run_kernel<KT>) == cudaSuccess) {
-                    const int regs = ((fa.numRegs + 7) / 8) * 8;
-                    int want = 65536 / (regs * KT::NT);
-                    if (want > 2048 / KT::NT) want = 2048 / KT::NT;
-                    if (want < 1) want = 1;
-                    const size_t need = (size_t)want * (KT::SMEM_BYTES + 1024);
-                    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-                    if (pct > 100) pct = 100;
-                    cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-                }
-                cudaGetLastError();
-            }
-            configured.fetch_or(bit, std::memory_order_release);
-        }
-    }
+    if (!ensure_configured<KT>()) return false;
     run_kernel<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
     return check(cudaGetLastError(), "kernel launch");
 }

@@ -136,16 +136,32 @@ template <typename T> B2_HD cx<T> sub_mi(cx<T> a, cx<T> b) {
 // renaming at the outermost load and store of a plan, every table stays "forward".
 template <typename T> B2_HD cx<T> swap_ri(cx<T> a) { return mk<T>(a.y, a.x); }
 
-// read-only global load through the non-coherent path on device (tables shared by all CTAs)
+// Table loads (stage twiddles, chirps, multipliers): read-only path, kept in L1 with evict-last priority.
+// Round-1 ncu (profiles/r1f_*) showed an L1 sector hit rate of 2 % with plain __ldg/__ldcs: the streaming
+// signal traffic was evicting the few KiB of twiddles every tile, so ~70 % of the twiddle loads went to L2.
 template <typename T> B2_HD cx<T> ldg(const cx<T>* p) {
 #if defined(__CUDA_ARCH__)
+    cx<T> r;
     if constexpr (sizeof(T) == 4) {
-        float2 v = __ldg(reinterpret_cast<const float2*>(p));
-        return mk<T>(v.x, v.y);
+        asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     } else {
-        double2 v = __ldg(reinterpret_cast<const double2*>(p));
-        return mk<T>(v.x, v.y);
+        asm("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     }
+    return r;
+#else
+    return *p;
+#endif
+}
+// large read-only tables that are streamed once per CTA (the N-entry inter-pass twiddle table): L2 only
+template <typename T> B2_HD cx<T> ldg_stream(const cx<T>* p) {
+#if defined(__CUDA_ARCH__)
+    cx<T> r;
+    if constexpr (sizeof(T) == 4) {
+        asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    } else {
+        asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    }
+    return r;
 #else
     return *p;
 #endif
@@ -158,16 +174,16 @@ B2_HD uint32_t ldg_u32(const uint32_t* p) {
 #endif
 }
 
-// streaming global load / store of signal data: read once, written once -> keep it out of L1
+// Signal data is read once and written once: do not allocate it in L1 at all.
 template <typename T> B2_HD cx<T> ld_stream(const cx<T>* p) {
 #if defined(__CUDA_ARCH__)
+    cx<T> r;
     if constexpr (sizeof(T) == 4) {
-        float2 v = __ldcs(reinterpret_cast<const float2*>(p));
-        return mk<T>(v.x, v.y);
+        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     } else {
-        double2 v = __ldcs(reinterpret_cast<const double2*>(p));
-        return mk<T>(v.x, v.y);
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     }
+    return r;
 #else
     return *p;
 #endif
@@ -175,9 +191,9 @@ template <typename T> B2_HD cx<T> ld_stream(const cx<T>* p) {
 template <typename T> B2_HD void st_stream(cx<T>* p, cx<T> v) {
 #if defined(__CUDA_ARCH__)
     if constexpr (sizeof(T) == 4) {
-        __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+        asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
     } else {
-        __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
     }
 #else
     *p = v;

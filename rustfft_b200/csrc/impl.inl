@@ -81,8 +81,6 @@ B2_TILE(float, 1024, 16, 8, 16, 16, 4)
 // radix-32 variants (f32): every four-step pass becomes two stages = one shared-memory exchange
 B2_TILE_V1(float, 512, 32, 16, 16, 32)
 B2_TILE_V1(float, 1024, 32, 8, 32, 32)
-B2_DIRECT_V1(float, 512, 32, 16, 16, 32)
-B2_DIRECT_V1(float, 1024, 32, 8, 32, 32)
 B2_DIRECT_V1(float, 8192, 32, 1, 16, 16, 32)
 B2_DIRECT_V1(float, 16384, 32, 1, 16, 32, 32)
 
@@ -113,6 +111,7 @@ struct b200fft_plan {
     uint64_t len = 0;
     int direction = 0, precision = 0, device = 0;
     std::string desc;
+    uint64_t chunk = 0;         // transforms per L2 chunk of multi-pass plans
     std::vector<void*> tables;  // device allocations owned by the plan
     std::function<bool(const b2::ExecCtx&)> exec;
     std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
@@ -151,6 +150,7 @@ static std::vector<cx<typename G::T>> stage_twiddles() {
     return tw;
 }
 
+static bool chunk_bytes_forced() { return std::getenv("B200FFT_CHUNK_MB") != nullptr; }
 static uint64_t chunk_bytes() {
     // target footprint of the L2-resident intermediate of multi-pass plans (B200 L2: ~126 MB)
     static uint64_t v = [] {
@@ -183,8 +183,8 @@ static bool use_radix32() {
     return v;
 }
 template <typename T, int L> struct HasV1 { static constexpr bool direct = false, tile = false; };
-template <> struct HasV1<float, 512> { static constexpr bool direct = true, tile = true; };
-template <> struct HasV1<float, 1024> { static constexpr bool direct = true, tile = true; };
+template <> struct HasV1<float, 512> { static constexpr bool direct = false, tile = true; };   // Direct{512,1024}:
+template <> struct HasV1<float, 1024> { static constexpr bool direct = false, tile = true; };  // radix-16 measured faster
 template <> struct HasV1<float, 8192> { static constexpr bool direct = true, tile = false; };
 template <> struct HasV1<float, 16384> { static constexpr bool direct = true, tile = false; };
 
@@ -263,7 +263,33 @@ struct Builder {
     struct PassFns {
         std::function<bool(const C* in, C* work, uint64_t nb, rt::stream_t)> a;
         std::function<bool(const C* work, C* out, uint64_t nb, rt::stream_t)> b;
+        uint64_t ctas_per_transform_a = 0, ctas_per_transform_b = 0;  // tiles per transform
+        int wave_a = 0, wave_b = 0;                                    // resident CTAs of each kernel
     };
+    // transforms per L2 chunk: inside [24, 80] MiB of workspace, as close to whole waves as possible for
+    // both passes (a 1024-CTA launch on 296 resident CTAs runs 3.46 waves = 13 % idle; 1152 CTAs run 3.89)
+    static uint64_t pick_chunk(uint64_t bytes_per_transform, const PassFns& f) {
+        if (chunk_bytes_forced()) return std::max<uint64_t>(1, chunk_bytes() / bytes_per_transform);
+        const uint64_t lo = std::max<uint64_t>(1, (24ull << 20) / bytes_per_transform);
+        const uint64_t hi = std::max<uint64_t>(lo, (80ull << 20) / bytes_per_transform);
+        uint64_t best = std::max<uint64_t>(1, (64ull << 20) / bytes_per_transform);
+        double best_eff = -1.0;
+        for (uint64_t nb = lo; nb <= hi; ++nb) {
+            double eff = 1.0;
+            const uint64_t cta[2] = {nb * f.ctas_per_transform_a, nb * f.ctas_per_transform_b};
+            const int wave[2] = {f.wave_a, f.wave_b};
+            for (int i = 0; i < 2; ++i) {
+                if (wave[i] <= 0) continue;
+                const double w = (double)cta[i] / wave[i];
+                eff = std::min(eff, w / std::ceil(w));
+            }
+            if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && nb > best && nb * bytes_per_transform <= (64ull << 20))) {
+                best_eff = eff;
+                best = nb;
+            }
+        }
+        return best;
+    }
     template <int L1, bool SW, int V = 0>
     static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, PassFns& fns) {
         if constexpr (V == 0 && HasV1<T, L1>::tile) {
@@ -273,6 +299,8 @@ struct Builder {
         using KT = FftKernel<G, FF, FF, LoadCols<T, SW>, StoreCols<T>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
+        fns.ctas_per_transform_a = ((1ull << lg2) + G::F - 1) / G::F;
+        fns.wave_a = rt::resident_ctas<KT>();
         fns.a = [=](const C* in, C* work, uint64_t nb, rt::stream_t s) {
             typename KT::Params p;
             p.load = LoadCols<T, SW>{in, lgN, lg2};
@@ -292,6 +320,8 @@ struct Builder {
         using KT = FftKernel<G, JF, FF, LoadRowsTw<T>, StoreTransposed<T, SW>>;
         const C* tw = upload(pl, stage_twiddles<G>());
         if (!tw) return false;
+        fns.ctas_per_transform_b = ((1ull << lg1) + G::F - 1) / G::F;
+        fns.wave_b = rt::resident_ctas<KT>();
         fns.b = [=](const C* work, C* out, uint64_t nb, rt::stream_t s) {
             if (use_pipelined() && (reinterpret_cast<uintptr_t>(work) & 15u) == 0) {
                 using KP = PipeKernel<G, FF, XformRowTw<T>, StoreTransposed<T, SW>>;
@@ -355,7 +385,7 @@ struct Builder {
         const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
-        const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / (N * sizeof(C)));
+        const uint64_t chunk = pick_chunk(N * sizeof(C), fns);
         pl.work_bytes = [=](uint64_t batch) { return std::min(batch, chunk) * N * sizeof(C); };
         pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
         pl.exec = [=](const ExecCtx& c) {
@@ -370,6 +400,7 @@ struct Builder {
             return true;
         };
         pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        pl.chunk = chunk;
         return true;
     }
 
@@ -744,12 +775,12 @@ static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uin
     const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
     const uint64_t batch = n_complex / pl->len;
     const uint64_t tbytes = pl->len * esz;
-    uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / tbytes);
+    uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / tbytes);
     if (chunk > batch) chunk = batch;
-    const int NBUF = 2;
-    void* dbuf[NBUF] = {nullptr, nullptr};
-    void* wbuf[NBUF] = {nullptr, nullptr};
-    rt::stream_t st[NBUF] = {nullptr, nullptr};
+    const int NBUF = 3;  // three chunks in flight keep H2D, kernels and D2H busy at the same time
+    void* dbuf[NBUF] = {nullptr, nullptr, nullptr};
+    void* wbuf[NBUF] = {nullptr, nullptr, nullptr};
+    rt::stream_t st[NBUF] = {nullptr, nullptr, nullptr};
     const uint64_t wbytes = pl->work_bytes(chunk);
     int rc = B200FFT_OK;
     for (int i = 0; i < NBUF && rc == B200FFT_OK; ++i) {

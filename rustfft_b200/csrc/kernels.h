@@ -91,7 +91,7 @@ struct StoreCols {
         return St{out + (b << lgN) + c, ok};
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
-        if (s.ok) s.p[(uint32_t)e << lg2] = v;
+        if (s.ok) st_stream(s.p + ((uint32_t)e << lg2), v);  // L1 bypass; stays in L2 (write-back) for pass B
     }
 };
 
@@ -114,7 +114,7 @@ struct LoadRowsTw {
     }
     B2_HD cx<T> get(const St& s, int e) const {
         if (!s.ok) return mk<T>(0, 0);
-        return cmul(ld_stream(s.p + e), ldg(s.t + e));
+        return cmul(ld_stream(s.p + e), ldg_stream(s.t + e));
     }
 };
 
@@ -444,7 +444,7 @@ struct XformRowTw {  // four-step pass B: times W_N^(k1*n2), table [k1][n2]
     uint32_t len, lg1;
     struct St { const cx<T>* t; };
     B2_HD St prep(uint64_t g) const { return St{tw + (g & ((1ull << lg1) - 1)) * (uint64_t)len}; }
-    B2_HD cx<T> apply(const St& s, int e, cx<T> v) const { return cmul(v, ldg(s.t + e)); }
+    B2_HD cx<T> apply(const St& s, int e, cx<T> v) const { return cmul(v, ldg_stream(s.t + e)); }
 };
 
 template <class G, Map M1, class Xform, class Store>

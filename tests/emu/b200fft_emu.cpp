@@ -64,6 +64,9 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t) {
     return true;
 }
 
+template <class KT>
+static int resident_ctas() { return 296; }  // what a B200 reports for a 2-CTA/SM kernel; only steers chunk sizes
+
 // persistent pipelined kernels: tiles in order; the TMA bulk copy of a tile becomes a memcpy
 template <class KT>
 static bool launch_pipelined(const typename KT::Params& p, stream_t) {
