@@ -174,14 +174,31 @@ B2_HD uint32_t ldg_u32(const uint32_t* p) {
 #endif
 }
 
-// Signal data is read once and written once: do not allocate it in L1 at all.
+// Signal data is read once and written once: no L1 allocation, and an L2 evict-first policy so that dead
+// lines (consumed input, finished output, the already-read half of the workspace) leave L2 before the
+// lines still waiting to be used.  The workspace written by a first pass gets the opposite hint
+// (evict-last) until the second pass has read it.
+#if defined(__CUDACC__)
+B2_D unsigned long long l2_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+B2_D unsigned long long l2_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif
 template <typename T> B2_HD cx<T> ld_stream(const cx<T>* p) {
 #if defined(__CUDA_ARCH__)
     cx<T> r;
     if constexpr (sizeof(T) == 4) {
-        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+                     : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(l2_evict_first()));
     } else {
-        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                     : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(l2_evict_first()));
     }
     return r;
 #else
@@ -191,9 +208,25 @@ template <typename T> B2_HD cx<T> ld_stream(const cx<T>* p) {
 template <typename T> B2_HD void st_stream(cx<T>* p, cx<T> v) {
 #if defined(__CUDA_ARCH__)
     if constexpr (sizeof(T) == 4) {
-        asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y),
+                     "l"(l2_evict_first()) : "memory");
     } else {
-        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y),
+                     "l"(l2_evict_first()) : "memory");
+    }
+#else
+    *p = v;
+#endif
+}
+// store into the L2-resident workspace that the next pass re-reads
+template <typename T> B2_HD void st_keep(cx<T>* p, cx<T> v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y),
+                     "l"(l2_evict_last()) : "memory");
+    } else {
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y),
+                     "l"(l2_evict_last()) : "memory");
     }
 #else
     *p = v;

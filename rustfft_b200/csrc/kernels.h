@@ -91,7 +91,7 @@ struct StoreCols {
         return St{out + (b << lgN) + c, ok};
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
-        if (s.ok) st_stream(s.p + ((uint32_t)e << lg2), v);  // L1 bypass; stays in L2 (write-back) for pass B
+        if (s.ok) st_keep(s.p + ((uint32_t)e << lg2), v);  // L1 bypass, L2 evict-last until pass B has read it
     }
 };
 
@@ -205,7 +205,7 @@ struct StoreTransposedConv {
                 x_out[s.b * (uint64_t)n] = SWAP ? swap_ri(dc) : dc;
                 w = w + conj(x0);
             }
-            s.p[k] = w;
+            st_keep(s.p + k, w);
         } else if (MODE == 1) {
             const cx<T> w = conj(v);
             s.p[ldg_u32(scatter + k)] = SWAP ? swap_ri(w) : w;
