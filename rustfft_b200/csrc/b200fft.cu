@@ -66,6 +66,15 @@ static stream_t stream_create() {
 }
 static void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
 static bool stream_sync(stream_t s) { return check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+typedef cudaEvent_t event_t;
+static event_t event_create() {
+    cudaEvent_t e = nullptr;
+    if (!check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    return e;
+}
+static void event_destroy(event_t e) { cudaEventDestroy(e); }
+static bool event_record(event_t e, stream_t s) { return check(cudaEventRecord(e, s), "cudaEventRecord"); }
+static bool stream_wait(stream_t s, event_t e) { return check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
 
 }  // namespace rt
 }  // namespace b2

@@ -218,6 +218,33 @@ template <typename T> B2_HD void st_stream(cx<T>* p, cx<T> v) {
     *p = v;
 #endif
 }
+// "cache streaming" forms (ld/st.global.cs): what the four-step passes use.  Measured A/B in round 1
+// (profiles/r1f vs r1g/r1h): the explicit no-allocate + L2-hint forms above are 3-5 points better for the
+// one-pass Direct kernels, the .cs forms 1-2 points better for the two L2-coupled passes.
+template <typename T> B2_HD cx<T> ld_cs(const cx<T>* p) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+        return mk<T>(v.x, v.y);
+    } else {
+        double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+        return mk<T>(v.x, v.y);
+    }
+#else
+    return *p;
+#endif
+}
+template <typename T> B2_HD void st_cs(cx<T>* p, cx<T> v) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4) {
+        __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+    } else {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+    }
+#else
+    *p = v;
+#endif
+}
 // store into the L2-resident workspace that the next pass re-reads
 template <typename T> B2_HD void st_keep(cx<T>* p, cx<T> v) {
 #if defined(__CUDA_ARCH__)

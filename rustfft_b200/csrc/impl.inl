@@ -113,11 +113,28 @@ struct b200fft_plan {
     std::string desc;
     uint64_t chunk = 0;         // transforms per L2 chunk of multi-pass plans
     std::vector<void*> tables;  // device allocations owned by the plan
+    // auxiliary streams for plans that run independent chunks on two streams (created lazily, reused)
+    std::mutex aux_mutex;
+    std::vector<b2::rt::stream_t> aux_streams;
+    b2::rt::stream_t aux_get() {
+        std::lock_guard<std::mutex> g(aux_mutex);
+        if (!aux_streams.empty()) {
+            b2::rt::stream_t s = aux_streams.back();
+            aux_streams.pop_back();
+            return s;
+        }
+        return b2::rt::stream_create();
+    }
+    void aux_put(b2::rt::stream_t s) {
+        std::lock_guard<std::mutex> g(aux_mutex);
+        aux_streams.push_back(s);
+    }
     std::function<bool(const b2::ExecCtx&)> exec;
     std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
     std::function<uint64_t(uint64_t)> launches = [](uint64_t) { return (uint64_t)0; };
     ~b200fft_plan() {
         for (void* p : tables) b2::rt::dfree(p);
+        for (auto s : aux_streams) b2::rt::stream_destroy(s);
     }
 };
 
@@ -170,6 +187,18 @@ static bool use_pipelined() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_PIPELINE");
         return e && std::atoi(e) == 1;
+    }();
+    return v;
+}
+
+// B200FFT_OVERLAP=0: all chunks of a multi-pass plan on the caller's stream.  Default: consecutive chunks
+// alternate between the caller's stream and an auxiliary one (two workspaces), so the tail of one chunk's
+// launches overlaps the head of the next chunk's -- chunks are independent, only pass A -> pass B within a
+// chunk is ordered.
+static bool use_overlap() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_OVERLAP");
+        return !(e && std::atoi(e) == 0);
     }();
     return v;
 }
@@ -386,19 +415,45 @@ struct Builder {
         const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
-        const uint64_t chunk = pick_chunk(N * sizeof(C), fns);
-        pl.work_bytes = [=](uint64_t batch) { return std::min(batch, chunk) * N * sizeof(C); };
+        const bool overlap = use_overlap();
+        // with two chunks in flight each gets half of the L2 budget
+        const uint64_t chunk = overlap ? std::max<uint64_t>(1, pick_chunk(N * sizeof(C), fns) / 2) : pick_chunk(N * sizeof(C), fns);
+        pl.work_bytes = [=](uint64_t batch) {
+            const uint64_t per = std::min(batch, chunk) * N * sizeof(C);
+            return (overlap && batch > chunk) ? 2 * per : per;
+        };
         pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+        b200fft_plan* self = &pl;
         pl.exec = [=](const ExecCtx& c) {
             const C* in = (const C*)c.in;
             C* out = (C*)c.out;
             C* work = (C*)c.work;
-            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
-                const uint64_t nb = std::min(chunk, c.batch - b0);
-                if (!fns.a(in + b0 * N, work, nb, c.stream)) return false;
-                if (!fns.b(work, out + b0 * N, nb, c.stream)) return false;
+            const bool two = overlap && c.batch > chunk;
+            rt::stream_t aux = nullptr;
+            rt::event_t ev_fork = nullptr, ev_join = nullptr;
+            if (two) {
+                aux = self->aux_get();
+                ev_fork = rt::event_create();
+                ev_join = rt::event_create();
+                if (!aux || !ev_fork || !ev_join) return false;
+                if (!rt::event_record(ev_fork, c.stream) || !rt::stream_wait(aux, ev_fork)) return false;
             }
-            return true;
+            bool ok = true;
+            uint64_t idx = 0;
+            for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                const bool odd = two && (idx & 1);
+                rt::stream_t s = odd ? aux : c.stream;
+                C* w = odd ? work + chunk * N : work;
+                ok = fns.a(in + b0 * N, w, nb, s) && fns.b(w, out + b0 * N, nb, s);
+            }
+            if (two) {
+                ok = rt::event_record(ev_join, aux) && rt::stream_wait(c.stream, ev_join) && ok;
+                rt::event_destroy(ev_fork);
+                rt::event_destroy(ev_join);
+                self->aux_put(aux);
+            }
+            return ok;
         };
         pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
         pl.chunk = chunk;

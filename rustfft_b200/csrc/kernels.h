@@ -74,7 +74,7 @@ struct LoadCols {
     }
     B2_HD cx<T> get(const St& s, int e) const {
         if (!s.ok) return mk<T>(0, 0);
-        cx<T> v = ld_stream(s.p + ((uint32_t)e << lg2));
+        cx<T> v = ld_cs(s.p + ((uint32_t)e << lg2));
         return SWAP ? swap_ri(v) : v;
     }
 };
@@ -91,7 +91,7 @@ struct StoreCols {
         return St{out + (b << lgN) + c, ok};
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
-        if (s.ok) st_keep(s.p + ((uint32_t)e << lg2), v);  // L1 bypass, L2 evict-last until pass B has read it
+        if (s.ok) s.p[(uint32_t)e << lg2] = v;  // plain write-back store: pass B re-reads it from L2
     }
 };
 
@@ -114,7 +114,7 @@ struct LoadRowsTw {
     }
     B2_HD cx<T> get(const St& s, int e) const {
         if (!s.ok) return mk<T>(0, 0);
-        return cmul(ld_stream(s.p + e), ldg_stream(s.t + e));
+        return cmul(ld_cs(s.p + e), ldg_stream(s.t + e));
     }
 };
 
@@ -130,7 +130,7 @@ struct StoreTransposed {
         return St{out + (b << lgN) + k1, ok};
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
-        if (s.ok) st_stream(s.p + ((uint32_t)e << lg1), SWAP ? swap_ri(v) : v);
+        if (s.ok) st_cs(s.p + ((uint32_t)e << lg1), SWAP ? swap_ri(v) : v);
     }
 };
 
@@ -205,7 +205,7 @@ struct StoreTransposedConv {
                 x_out[s.b * (uint64_t)n] = SWAP ? swap_ri(dc) : dc;
                 w = w + conj(x0);
             }
-            st_keep(s.p + k, w);
+            s.p[k] = w;
         } else if (MODE == 1) {
             const cx<T> w = conj(v);
             s.p[ldg_u32(scatter + k)] = SWAP ? swap_ri(w) : w;

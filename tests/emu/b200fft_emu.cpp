@@ -32,6 +32,11 @@ static void free_async(void* p, stream_t) { std::free(p); }
 static stream_t stream_create() { return (stream_t)1; }
 static void stream_destroy(stream_t) {}
 static bool stream_sync(stream_t) { return true; }
+typedef void* event_t;
+static event_t event_create() { return (event_t)1; }
+static void event_destroy(event_t) {}
+static bool event_record(event_t, stream_t) { return true; }
+static bool stream_wait(stream_t, event_t) { return true; }
 }  // namespace rt
 }  // namespace b2
 
