@@ -335,6 +335,70 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "how": "b200fft_exec_host_outofplace on pinned host buffers (wall clock incl. H2D+D2H), "
                       f"{args.e2e_pinned_gib} GiB pinned window reused per call"}
 
+    # ---- the other BASELINE configs, device resident, informational (not part of `value`) --------------
+    extras = None
+    if not args.no_extras:
+        extras = []
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        # config 3: f64 forward + inverse round trip, N = 1234, batch = 1024 (in place)
+        p64 = rb.FftPlanner(np.complex128, device=local_rank)
+        f3, i3 = p64.plan_fft_forward(1234), p64.plan_fft_inverse(1234)
+        x3 = torch.view_as_complex(torch.rand(64 * 1024 * 1234, 2, device=dev, dtype=torch.float64)).contiguous()
+
+        def c3():
+            for k in range(64):  # 64 distinct 19 MiB batches (1.2 GiB): no L2 reuse between calls
+                sl = x3[k * 1024 * 1234:(k + 1) * 1024 * 1234]
+                f3.process_device(sl)
+                i3.process_device(sl)
+
+        ms = timed(c3, 2) / 64
+        extras.append({"config": "f64 forward+inverse N=1234 batch=1024", "plan": f3.describe(), "ms": round(ms, 4),
+                       "gflops": round(2 * 5 * 1234 * math.log2(1234) * 1024 / (ms * 1e-3) / 1e9, 1),
+                       "frac": round(2 * 32.0 * 1234 * 1024 / (ms * 1e-3) / 1e9 / hbm, 4)})
+        del x3
+        # config 4: f32 prime N = 65537, batch = 512
+        f4 = planner.plan_fft_forward(65537)
+        x4 = src[: 8 * 512 * 65537]
+        y4 = dst[: 8 * 512 * 65537]
+
+        def c4():
+            for k in range(8):  # 8 distinct 256 MiB batches
+                f4.process_device(x4[k * 512 * 65537:(k + 1) * 512 * 65537], out=y4[k * 512 * 65537:(k + 1) * 512 * 65537])
+
+        ms = timed(c4, 2) / 8
+        extras.append({"config": "f32 prime N=65537 batch=512", "plan": f4.describe(), "ms": round(ms, 4),
+                       "gflops": round(5 * 65537 * math.log2(65537) * 512 / (ms * 1e-3) / 1e9, 1),
+                       "frac": round(16.0 * 65537 * 512 / (ms * 1e-3) / 1e9 / hbm, 4)})
+        # config 5: f32 N = 2^16, batch = 65536 sharded over the ranks of this job (65536 / world per GPU)
+        per_rank = 65536 // world
+        f5 = plans[16]
+        ws5 = torch.empty(max(f5.workspace_bytes(per_rank), 16), dtype=torch.uint8, device=dev)
+
+        def c5():
+            f5.process_device(src[: per_rank << 16], out=dst[: per_rank << 16], workspace=ws5)
+
+        barrier()
+        ms = timed(c5, 2)
+        if dist:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        extras.append({"config": f"f32 N=2^16 batch=65536 sharded over {world} GPU(s) ({per_rank} per GPU, shards resident)",
+                       "plan": f5.describe(), "ms": round(ms, 4),
+                       "gflops": round(5 * 65536 * 16 * 65536 / (ms * 1e-3) / 1e9, 1),
+                       "frac_per_gpu": round(16.0 * 65536 * per_rank / (ms * 1e-3) / 1e9 / hbm, 4)})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle
@@ -363,7 +427,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "kernel": "whole step (every launch in it is one of this repo's FFT passes); "
                                    "dominant = FourStep{1024x1024} passes A+B at N=2^20",
                          "algorithmic_bytes_per_step": int(step_bytes)},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "other_configs": extras,
         }), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -378,6 +442,7 @@ def main():
     ap.add_argument("--logs", default="", help="comma list of log2 sizes (debug); default 10..20")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational timings of BASELINE configs 3-5")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-pinned-gib", type=float, default=4.0)
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
@@ -386,6 +451,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.profile or args.logs:
+        args.no_extras = True
     if args.profile:
         args.no_e2e = args.no_cpu = True
     if args.impl == "reference":

@@ -202,6 +202,16 @@ static bool use_overlap() {
     }();
     return v;
 }
+// number of streams the chunks of a multi-pass plan are spread over (B200FFT_STREAMS, default 2, max 4)
+static int overlap_streams() {
+    static int v = [] {
+        if (!use_overlap()) return 1;
+        const char* e = std::getenv("B200FFT_STREAMS");
+        int k = e ? std::atoi(e) : 2;
+        return k < 1 ? 1 : (k > 4 ? 4 : k);
+    }();
+    return v;
+}
 
 // B200FFT_RADIX32=0 disables the radix-32 geometries (A/B measurements)
 static bool use_radix32() {
@@ -415,12 +425,13 @@ struct Builder {
         const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
-        const bool overlap = use_overlap();
-        // with two chunks in flight each gets half of the L2 budget
-        const uint64_t chunk = overlap ? std::max<uint64_t>(1, pick_chunk(N * sizeof(C), fns) / 2) : pick_chunk(N * sizeof(C), fns);
+        const int K = overlap_streams();
+        // K chunks in flight share the L2 budget
+        const uint64_t chunk = std::max<uint64_t>(1, pick_chunk(N * sizeof(C), fns) / (uint64_t)K);
         pl.work_bytes = [=](uint64_t batch) {
             const uint64_t per = std::min(batch, chunk) * N * sizeof(C);
-            return (overlap && batch > chunk) ? 2 * per : per;
+            const uint64_t nchunks = (batch + chunk - 1) / chunk;
+            return per * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
         };
         pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
         b200fft_plan* self = &pl;
@@ -428,30 +439,34 @@ struct Builder {
             const C* in = (const C*)c.in;
             C* out = (C*)c.out;
             C* work = (C*)c.work;
-            const bool two = overlap && c.batch > chunk;
-            rt::stream_t aux = nullptr;
-            rt::event_t ev_fork = nullptr, ev_join = nullptr;
-            if (two) {
-                aux = self->aux_get();
+            const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
+            const int ns = (int)std::min<uint64_t>((uint64_t)K, nchunks);  // streams actually used
+            rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
+            rt::event_t ev_fork = nullptr;
+            if (ns > 1) {
                 ev_fork = rt::event_create();
-                ev_join = rt::event_create();
-                if (!aux || !ev_fork || !ev_join) return false;
-                if (!rt::event_record(ev_fork, c.stream) || !rt::stream_wait(aux, ev_fork)) return false;
+                if (!ev_fork || !rt::event_record(ev_fork, c.stream)) return false;
+                for (int k = 1; k < ns; ++k) {
+                    st[k] = self->aux_get();
+                    if (!st[k] || !rt::stream_wait(st[k], ev_fork)) return false;
+                }
             }
             bool ok = true;
             uint64_t idx = 0;
             for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
                 const uint64_t nb = std::min(chunk, c.batch - b0);
-                const bool odd = two && (idx & 1);
-                rt::stream_t s = odd ? aux : c.stream;
-                C* w = odd ? work + chunk * N : work;
-                ok = fns.a(in + b0 * N, w, nb, s) && fns.b(w, out + b0 * N, nb, s);
+                const int k = (int)(idx % (uint64_t)ns);
+                C* w = work + (uint64_t)k * chunk * N;
+                ok = fns.a(in + b0 * N, w, nb, st[k]) && fns.b(w, out + b0 * N, nb, st[k]);
             }
-            if (two) {
-                ok = rt::event_record(ev_join, aux) && rt::stream_wait(c.stream, ev_join) && ok;
+            if (ns > 1) {
+                for (int k = 1; k < ns; ++k) {
+                    rt::event_t ev = rt::event_create();
+                    ok = ev && rt::event_record(ev, st[k]) && rt::stream_wait(c.stream, ev) && ok;
+                    if (ev) rt::event_destroy(ev);
+                    self->aux_put(st[k]);
+                }
                 rt::event_destroy(ev_fork);
-                rt::event_destroy(ev_join);
-                self->aux_put(aux);
             }
             return ok;
         };
@@ -590,22 +605,51 @@ struct Builder {
         PassFns plain;
         const bool ok = pl.direction ? make_conv_rt<true>(pl, t, f, plain) : make_conv_rt<false>(pl, t, f, plain);
         if (!ok) return false;
-        const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / 2 / (M * sizeof(C)));
-        pl.work_bytes = [=](uint64_t batch) { return 2 * std::min(batch, chunk) * M * sizeof(C); };
+        const int K = overlap_streams();
+        // two workspaces per chunk, K chunks in flight, all inside the L2 budget
+        const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes() / 2 / (uint64_t)K / (M * sizeof(C)));
+        pl.work_bytes = [=](uint64_t batch) {
+            const uint64_t nchunks = (batch + chunk - 1) / chunk;
+            return 2 * std::min(batch, chunk) * M * sizeof(C) * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
+        };
         pl.launches = [=](uint64_t batch) { return 4 * ((batch + chunk - 1) / chunk); };
+        b200fft_plan* self = &pl;
         pl.exec = [=](const ExecCtx& c) {
             const C* in = (const C*)c.in;
             C* out = (C*)c.out;
-            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
-                const uint64_t nb = std::min(chunk, c.batch - b0);
-                C* w1 = (C*)c.work;
-                C* w2 = w1 + std::min(c.batch, chunk) * M;
-                if (!f.a1(in + b0 * n, w1, nb, c.stream)) return false;
-                if (!f.b1(w1, w2, in + b0 * n, out + b0 * n, nb, c.stream)) return false;
-                if (!plain.a(w2, w2, nb, c.stream)) return false;
-                if (!f.b2(w2, out + b0 * n, nb, c.stream)) return false;
+            const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
+            const int ns = (int)std::min<uint64_t>((uint64_t)K, nchunks);
+            const uint64_t per = std::min(c.batch, chunk) * M;  // elements of one workspace
+            rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
+            rt::event_t ev_fork = nullptr;
+            if (ns > 1) {
+                ev_fork = rt::event_create();
+                if (!ev_fork || !rt::event_record(ev_fork, c.stream)) return false;
+                for (int k = 1; k < ns; ++k) {
+                    st[k] = self->aux_get();
+                    if (!st[k] || !rt::stream_wait(st[k], ev_fork)) return false;
+                }
             }
-            return true;
+            bool ok = true;
+            uint64_t idx = 0;
+            for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                const int k = (int)(idx % (uint64_t)ns);
+                C* w1 = (C*)c.work + (uint64_t)k * 2 * per;
+                C* w2 = w1 + per;
+                ok = f.a1(in + b0 * n, w1, nb, st[k]) && f.b1(w1, w2, in + b0 * n, out + b0 * n, nb, st[k]) &&
+                     plain.a(w2, w2, nb, st[k]) && f.b2(w2, out + b0 * n, nb, st[k]);
+            }
+            if (ns > 1) {
+                for (int k = 1; k < ns; ++k) {
+                    rt::event_t ev = rt::event_create();
+                    ok = ev && rt::event_record(ev, st[k]) && rt::stream_wait(c.stream, ev) && ok;
+                    if (ev) rt::event_destroy(ev);
+                    self->aux_put(st[k]);
+                }
+                rt::event_destroy(ev_fork);
+            }
+            return ok;
         };
         const std::string inner = "FourStep{" + std::to_string(1u << t.lg1) + "x" + std::to_string(1u << t.lg2) + "}";
         pl.desc = rader ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + "}"
