@@ -143,6 +143,29 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
     return check(cudaGetLastError(), "kernel launch");
 }
 
+// kernels with run-time sized dynamic shared memory (<= max_smem bytes, configured once)
+template <class KT>
+static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_bytes, size_t max_smem, stream_t s) {
+    if (ctas == 0) return true;
+    if (ctas > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        if (!check(cudaFuncSetAttribute(run_kernel_dyn<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return false;
+        cudaFuncSetAttribute(run_kernel_dyn<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    run_kernel_dyn<KT><<<(unsigned)ctas, KT::NT, smem_bytes, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
 // persistent pipelined kernels: grid = SMs x resident CTAs (queried once per kernel and device)
 template <class KT>
 static bool launch_pipelined(const typename KT::Params& p, stream_t s) {

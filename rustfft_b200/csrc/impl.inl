@@ -7,6 +7,7 @@
 //   len 0, 1                      -> Identity
 //   2^k <= 16384 (f64: 8192)      -> Direct      one CTA pass, Stockham radix-4/8/16 in registers+smem
 //   larger 2^k (<= 2^20)          -> FourStep    two passes, intermediate kept in L2 by chunking
+//   2^a 3^b 5^c 7^d <= 4096       -> Smooth      one CTA pass, run-time radix list (16/8/4/2/7/5/3)
 //   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= 256, else over FourStep)
 //   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= 4096)
 #include <cstdio>
@@ -657,6 +658,71 @@ struct Builder {
         return true;
     }
 
+    // ---------------- Smooth (7-smooth lengths without a compiled geometry) ----------------
+    static constexpr uint32_t SMOOTH_MAX = sizeof(T) == 4 ? 4096 : 2048;  // 2 * n * sizeof(C) <= 64 KiB
+    static bool smooth_factor(uint64_t n, std::vector<uint32_t>& radices) {
+        uint32_t a = 0, b = 0, c = 0, d = 0;
+        while (n % 2 == 0) { n /= 2; ++a; }
+        while (n % 3 == 0) { n /= 3; ++b; }
+        while (n % 5 == 0) { n /= 5; ++c; }
+        while (n % 7 == 0) { n /= 7; ++d; }
+        if (n != 1) return false;
+        // largest radices first (fewest shared-memory passes); odd radices after the powers of two
+        while (a >= 4) { radices.push_back(16); a -= 4; }
+        if (a == 3) radices.push_back(8);
+        if (a == 2) radices.push_back(4);
+        if (a == 1) radices.push_back(2);
+        for (uint32_t i = 0; i < d; ++i) radices.push_back(7);
+        for (uint32_t i = 0; i < c; ++i) radices.push_back(5);
+        for (uint32_t i = 0; i < b; ++i) radices.push_back(3);
+        return !radices.empty() && radices.size() <= 8;
+    }
+    template <bool SW>
+    static bool make_smooth_t(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
+        using KT = SmoothKernel<T, SW>;
+        const uint32_t n = (uint32_t)pl.len;
+        typename KT::Params base;
+        std::memset(&base, 0, sizeof(base));
+        std::vector<C> tw;
+        uint32_t p = 1;
+        for (size_t s = 0; s < radices.size(); ++s) {
+            const uint32_t R = radices[s];
+            base.radix[s] = R;
+            base.tw_off[s] = (uint32_t)tw.size();
+            if (s >= 1)
+                for (uint32_t r = 1; r < R; ++r)
+                    for (uint32_t k = 0; k < p; ++k) tw.push_back(hm::twiddle<T>((uint64_t)k * r, (uint64_t)p * R));
+            p *= R;
+        }
+        if (tw.empty()) tw.push_back(mk<T>(1, 0));
+        const C* d_tw = upload(pl, tw);
+        if (!d_tw) return false;
+        base.tw = d_tw;
+        base.n = n;
+        base.n_stages = (uint32_t)radices.size();
+        // transforms per CTA: fill 256 threads with butterflies of the smallest stage, stay inside 64 KiB
+        uint32_t F = std::max<uint32_t>(1, SMOOTH_MAX / n);
+        if (F > 64) F = 64;
+        base.f_per_cta = F;
+        base.smem_bytes = radices.size() > 1 ? (uint32_t)(2ull * F * n * sizeof(C)) : 0;
+        const size_t max_smem = 2ull * SMOOTH_MAX * sizeof(C);
+        pl.exec = [=](const ExecCtx& c) {
+            typename KT::Params q = base;
+            q.in = (const C*)c.in;
+            q.out = (C*)c.out;
+            q.n_fft = c.batch;
+            return rt::launch_dyn<KT>(q, (c.batch + F - 1) / F, q.smem_bytes, max_smem, c.stream);
+        };
+        pl.launches = [](uint64_t) { return (uint64_t)1; };
+        std::string rs;
+        for (size_t s = 0; s < radices.size(); ++s) rs += (s ? "x" : "") + std::to_string(radices[s]);
+        pl.desc = "Smooth{" + std::to_string(n) + "=" + rs + "}";
+        return true;
+    }
+    static bool make_smooth(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
+        return pl.direction ? make_smooth_t<true>(pl, radices) : make_smooth_t<false>(pl, radices);
+    }
+
     // ---------------- Bluestein (fused) ----------------
     static void bluestein_tables(uint64_t n, uint64_t M, std::vector<C>& chirp, std::vector<C>& mult) {
         chirp.resize((size_t)n);
@@ -804,6 +870,8 @@ struct Builder {
                 ok = make_four_step(pl, hm::ilog2(n));
             else
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^20 are not planned by this build");
+        } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
+            ok = make_smooth(pl, radices);  // 2^a 3^b 5^c 7^d
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {

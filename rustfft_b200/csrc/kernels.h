@@ -418,6 +418,95 @@ struct RaderKernel {
 };
 
 // ------------------------------------------------------------------------------------------
+// SmoothKernel: one-pass Stockham FFT for 7-smooth lengths n = 2^a 3^b 5^c 7^d that have no compiled
+// geometry (n <= SMOOTH_MAX).  The radix list is run-time data (the host planner factors n into
+// stages of radix 16/8/4/2/3/5/7 -- the reference's RadixN does the same with 2..7 over a butterfly base,
+// src/algorithm/radixn.rs:54-155, src/plan.rs:508-607); each stage is one pass over a ping-pong pair of
+// shared-memory buffers, the first stage reads global memory and the last one writes it, both coalesced
+// and in natural order (same index algebra as engine.h).  Slower per element than the compiled
+// power-of-two geometries (no cross-stage register reuse, generic index arithmetic) but one pass over
+// HBM and no padding to a power of two -- against Bluestein's two FFTs of 2-4x the length.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SWAP>
+struct SmoothKernel {
+    using T_ = T;
+    static constexpr int NT = 256;
+    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int NPHASE = MAX_STAGES;
+    static constexpr size_t SMEM_BYTES = 0;  // run-time sized: Params::smem_bytes
+    struct Params {
+        const cx<T>* in;
+        cx<T>* out;
+        const cx<T>* tw;  // packed like the engine's: stage s >= 1 at tw_off[s], entry (r-1)*p + k = W_{pR}^{k r}
+        uint64_t n_fft;
+        uint32_t n, n_stages, f_per_cta, smem_bytes;
+        uint32_t radix[MAX_STAGES];
+        uint32_t tw_off[MAX_STAGES];
+    };
+    struct Regs {};
+
+    template <int R>
+    static B2_HD void stage(const Params& p, uint32_t bid, int tid, int s, cx<T>* smem) {
+        const uint32_t n = p.n, F = p.f_per_cta;
+        uint32_t pp = 1;  // product of the radices before stage s
+        for (int i = 0; i < s; ++i) pp *= p.radix[i];
+        const uint32_t T_s = n / R;  // butterflies per transform
+        const bool first = (s == 0), last = (s == (int)p.n_stages - 1);
+        const cx<T>* src_buf = smem + (size_t)((s + 1) & 1) * F * n;  // stage s-1 wrote buffer (s-1)&1
+        cx<T>* dst_buf = smem + (size_t)(s & 1) * F * n;
+        const cx<T>* tws = p.tw + p.tw_off[s];
+        for (uint32_t b = (uint32_t)tid; b < F * T_s; b += NT) {
+            const uint32_t f = b / T_s, i = b - f * T_s;
+            const uint64_t g = (uint64_t)bid * F + f;
+            if (g >= p.n_fft) continue;
+            const uint32_t k = i % pp;
+            cx<T> a[R];
+            if (first) {
+                const cx<T>* src = p.in + g * (uint64_t)n + i;
+                B2_UNROLL
+                for (int q = 0; q < R; ++q) {
+                    cx<T> v = ld_stream(src + (size_t)q * T_s);
+                    a[q] = SWAP ? swap_ri(v) : v;
+                }
+            } else {
+                const cx<T>* src = src_buf + (size_t)f * n + i;
+                B2_UNROLL
+                for (int q = 0; q < R; ++q) a[q] = src[(size_t)q * T_s];
+                B2_UNROLL
+                for (int q = 1; q < R; ++q) a[q] = cmul(a[q], ldg(tws + (size_t)(q - 1) * pp + k));
+            }
+            Bfly<R, T>::run(a);
+            const uint32_t base = (i - k) * R + k;
+            if (last) {
+                cx<T>* dst = p.out + g * (uint64_t)n + base;
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) st_stream(dst + (size_t)m * pp, SWAP ? swap_ri(a[m]) : a[m]);
+            } else {
+                cx<T>* dst = dst_buf + (size_t)f * n + base;
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) dst[(size_t)m * pp] = a[m];
+            }
+        }
+    }
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs&, cx<T>* smem) {
+        if (P >= (int)p.n_stages) return;
+        switch (p.radix[P]) {
+            case 2: stage<2>(p, bid, tid, P, smem); break;
+            case 3: stage<3>(p, bid, tid, P, smem); break;
+            case 4: stage<4>(p, bid, tid, P, smem); break;
+            case 5: stage<5>(p, bid, tid, P, smem); break;
+            case 7: stage<7>(p, bid, tid, P, smem); break;
+            case 8: stage<8>(p, bid, tid, P, smem); break;
+            case 16: stage<16>(p, bid, tid, P, smem); break;
+            default: break;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Persistent, software-pipelined one-pass kernels (contiguous tiles).
 //
 // A tile = F whole FFTs that are contiguous in global memory (Direct: F transforms; four-step pass B:
@@ -523,6 +612,14 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel(const __gri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));
+}
+
+// same, for kernels whose shared-memory size is run-time data (SmoothKernel)
+template <class KT>
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const __grid_constant__ typename KT::Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename KT::Regs r;
+    PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T_>*>(smem_raw));
 }
 
 template <class KT>

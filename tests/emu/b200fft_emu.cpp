@@ -49,8 +49,8 @@ static uint64_t g_launches = 0;
 
 template <class KT, int P>
 struct EmuPhases {
-    static void run(const typename KT::Params& p, uint32_t bid, std::vector<typename KT::Regs>& regs,
-                    cx<typename KT::T>* smem) {
+    template <class S>
+    static void run(const typename KT::Params& p, uint32_t bid, std::vector<typename KT::Regs>& regs, S* smem) {
         for (int tid = 0; tid < KT::NT; ++tid) KT::template phase<P>(p, bid, tid, regs[(size_t)tid], smem);
         if constexpr (P + 1 < KT::NPHASE) EmuPhases<KT, P + 1>::run(p, bid, regs, smem);
     }
@@ -62,6 +62,18 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t) {
     std::vector<typename KT::Regs> regs((size_t)KT::NT);
     // poison shared memory so a read of a slot nobody wrote shows up as NaN
     std::vector<cx<typename KT::T>> smem(KT::SMEM_BYTES / sizeof(cx<typename KT::T>) + 1);
+    for (uint64_t bid = 0; bid < ctas; ++bid) {
+        std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
+        EmuPhases<KT, 0>::run(p, (uint32_t)bid, regs, smem.data());
+    }
+    return true;
+}
+
+template <class KT>
+static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_bytes, size_t, stream_t) {
+    ++g_launches;
+    std::vector<typename KT::Regs> regs((size_t)KT::NT);
+    std::vector<cx<typename KT::T_>> smem(smem_bytes / sizeof(cx<typename KT::T_>) + 1);
     for (uint64_t bid = 0; bid < ctas; ++bid) {
         std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
         EmuPhases<KT, 0>::run(p, (uint32_t)bid, regs, smem.data());

@@ -35,7 +35,17 @@ def test_sampled_lens_up_to_1000_and_plan_kinds(planner):
     for n in list(range(201, 1001, 37)) + [255, 256, 257, 511, 512, 617, 719, 991, 997, 1000, 1024, 1234, 2047, 2048]:
         f = check_fft_algorithm(pl, n, DIRS[n % 2], dtype)
         seen.add(f.describe().split("{")[0])
-    assert {"Direct", "Bluestein", "Rader"} <= seen
+    assert {"Direct", "Bluestein", "Rader", "Smooth"} <= seen
+
+
+@pytest.mark.parametrize("n,desc", [(6, "Smooth{6=2x3}"), (1000, "Smooth{1000=8x5x5x5}"), (343, "Smooth{343=7x7x7}"),
+                                    (1536, "Smooth{1536=16x16x2x3}"), (7, "Smooth{7=7}"), (105, "Smooth{105=7x5x3}")])
+def test_smooth_plans(planner, n, desc):
+    """7-smooth lengths run natively (radix 16/8/4/2/7/5/3 stages), cf. RadixN in src/algorithm/radixn.rs."""
+    pl, dtype = planner
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=5)
+    assert f.describe() == desc
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=70)  # > F transforms: several CTAs
 
 
 @pytest.mark.parametrize("n,desc32,desc64", [

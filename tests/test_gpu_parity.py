@@ -129,10 +129,20 @@ def test_large_non_power_of_two(planner, n):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
+@pytest.mark.parametrize("n", [360, 1000, 1200, 1536, 2000, 2401, 3600, 4000])
+def test_smooth_lengths_native(planner, n):
+    """2^a 3^b 5^c 7^d: one-pass run-time-radix kernel (the reference: RadixN / MixedRadix, plan.rs:508-607)."""
+    pl, dtype = planner
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=300)
+    if n <= 2048 or dtype == np.complex64:
+        assert f.describe().startswith("Smooth{")
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=3)
+
+
 def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
     torch = torch_cuda
     pl = rb.FftPlanner(np.complex64)
-    for n, batch in [(1024, 33), (1 << 14, 5), (1 << 15, 300), (1 << 16, 5), (257, 9), (1000, 17), (65537, 80), (5000, 3)]:
+    for n, batch in [(1024, 33), (1 << 14, 5), (1 << 15, 300), (1 << 16, 5), (257, 9), (1000, 17), (997, 17), (65537, 80), (5000, 3)]:
         f = pl.plan_fft_forward(n)
         x = signal(n * batch, np.complex64, seed=n)
         host = x.copy()
