@@ -236,8 +236,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         else:
             one_size(lg)
 
-    for lg in logs:  # one more warm-up through the final launch path
-        run_size(lg)
+    if not args.profile:
+        for lg in logs:  # one more warm-up through the final launch path
+            run_size(lg)
     barrier()
 
     sampler = ClockSampler(local_rank)
