@@ -946,7 +946,12 @@ static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uin
     const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
     const uint64_t batch = n_complex / pl->len;
     const uint64_t tbytes = pl->len * esz;
-    uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / tbytes);
+    static const uint64_t host_chunk_bytes = [] {
+        const char* e = std::getenv("B200FFT_HOST_CHUNK_MB");  // staging granularity (tests shrink it)
+        const uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 64;
+        return (mb < 1 ? 1 : mb) << 20;
+    }();
+    uint64_t chunk = std::max<uint64_t>(1, host_chunk_bytes / tbytes);
     if (chunk > batch) chunk = batch;
     const uint64_t nchunks = (batch + chunk - 1) / chunk;
     const int NB = (int)std::min<uint64_t>(4, nchunks);

@@ -95,6 +95,22 @@ def test_chunked_four_step_matches_unchunked(lib):
         assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * 16
 
 
+def test_host_pipeline_ring_wraps(lib):
+    """The host-slice path stages 1 MiB chunks here (tests/util.py): 11 chunks through a ring of 4 device
+    buffers, in place and out of place, with a ragged last chunk."""
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    n, batch = 1024, 1350  # 8 KiB per transform -> 128 per chunk -> 11 chunks, last one ragged
+    f = pl.plan_fft_forward(n)
+    x = signal(n * batch, np.complex64, seed=9)
+    a = x.copy()
+    f.process(a)
+    b = np.zeros_like(x)
+    f.process_outofplace_with_scratch(x.copy(), b)
+    assert np.array_equal(a, b)
+    for t in (0, 127, 128, 1000, 1349):
+        assert rel_l2(a[t * n:(t + 1) * n], truth(x[t * n:(t + 1) * n], n, False)) < 4 * 5.96e-8 * 10
+
+
 def test_error_behaviour_and_cache(planner):
     pl, dtype = planner
     check_error_behaviour(pl, dtype)

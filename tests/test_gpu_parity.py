@@ -164,6 +164,23 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
                 f.process_device(d2, workspace=ws[: nbytes // 2])
 
 
+def test_host_pipeline_many_chunks(torch_cuda):
+    """Host-slice path with more 64 MiB staging chunks than ring slots (4): 6.x chunks, pageable and pinned."""
+    torch = torch_cuda
+    pl = rb.FftPlanner(np.complex64)
+    n, batch = 4096, 6 * 2048 + 77
+    f = pl.plan_fft_forward(n)
+    x = signal(n * batch, np.complex64, seed=12)
+    a = x.copy()
+    f.process(a)  # pageable
+    pin_in = torch.from_numpy(x).pin_memory()
+    pin_out = torch.empty_like(pin_in).pin_memory()
+    f.process_outofplace_with_scratch(pin_in.numpy(), pin_out.numpy())
+    assert np.array_equal(a, pin_out.numpy())
+    for t in (0, 2047, 2048, 8191, batch - 1):
+        assert rel_l2(a[t * n:(t + 1) * n], truth(x[t * n:(t + 1) * n], n, False)) <= strict_bound(n, np.complex64)
+
+
 def test_error_behaviour_and_cache(planner):
     pl, dtype = planner
     check_error_behaviour(pl, dtype)

@@ -48,4 +48,5 @@ def emu_library():
     import rustfft_b200 as rb
 
     os.environ.setdefault("B200FFT_CHUNK_MB", "32")  # read once by the library; pins the chunking the tests assert
+    os.environ.setdefault("B200FFT_HOST_CHUNK_MB", "1")  # small staging chunks: the host ring wraps in cheap tests
     return rb.Library(ge.build_emu())
