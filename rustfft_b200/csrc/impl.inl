@@ -933,12 +933,18 @@ static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_ou
     return B200FFT_OK;
 }
 
-// Host-slice path: a three-stage pipeline over a ring of device buffers.  One stream only copies in,
-// one only computes, one only copies out, ordered per chunk by events, so the H2D engine, the SMs and
-// the D2H engine all stay busy (both PCIe directions at once) when the caller's memory is pinned.
-// (A two-stream H2D->kernel->D2H design measured 37 GB/s per direction in round 1: each stream's next
-// H2D had to wait for its own previous D2H.)
-static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
+// Host-slice path: chunks of the batch flow H2D -> kernels -> D2H on two streams with two device
+// buffers, so copies in both directions overlap compute when the caller's memory is pinned.
+static uint64_t host_chunk_bytes_cfg() {
+    static const uint64_t v = [] {
+        const char* e = std::getenv("B200FFT_HOST_CHUNK_MB");  // staging granularity (tests shrink it)
+        const uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 64;
+        return (mb < 1 ? 1 : mb) << 20;
+    }();
+    return v;
+}
+
+static int exec_host_impl_2stream(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
     if (!pl) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
     if (pl->len == 0 || n_complex == 0) return B200FFT_OK;
     if (!in || !out) return fail(B200FFT_ERR_INVALID_ARG, "null buffer");
@@ -946,12 +952,59 @@ static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uin
     const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
     const uint64_t batch = n_complex / pl->len;
     const uint64_t tbytes = pl->len * esz;
-    static const uint64_t host_chunk_bytes = [] {
-        const char* e = std::getenv("B200FFT_HOST_CHUNK_MB");  // staging granularity (tests shrink it)
-        const uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 64;
-        return (mb < 1 ? 1 : mb) << 20;
+    uint64_t chunk = std::max<uint64_t>(1, host_chunk_bytes_cfg() / tbytes);
+    if (chunk > batch) chunk = batch;
+    const int NBUF = 2;  // (three 32 MiB buffers measured slower: 2.50 s vs 1.86 s per sweep step, round 1)
+    void* dbuf[NBUF] = {nullptr, nullptr};
+    void* wbuf[NBUF] = {nullptr, nullptr};
+    rt::stream_t st[NBUF] = {nullptr, nullptr};
+    const uint64_t wbytes = pl->work_bytes(chunk);
+    int rc = B200FFT_OK;
+    for (int i = 0; i < NBUF && rc == B200FFT_OK; ++i) {
+        st[i] = rt::stream_create();
+        dbuf[i] = rt::dmalloc(chunk * tbytes);
+        if (wbytes) wbuf[i] = rt::dmalloc(wbytes);
+        if (!st[i] || !dbuf[i] || (wbytes && !wbuf[i])) rc = fail(B200FFT_ERR_CUDA, "staging allocation failed: " + rt::last_error());
+    }
+    uint64_t idx = 0;
+    for (uint64_t b0 = 0; b0 < batch && rc == B200FFT_OK; b0 += chunk, ++idx) {
+        const int s = (int)(idx % NBUF);
+        const uint64_t nb = std::min(chunk, batch - b0);
+        const char* src = (const char*)in + b0 * tbytes;
+        char* dst = (char*)out + b0 * tbytes;
+        if (!rt::h2d_async(dbuf[s], src, nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
+        rc = exec_device_impl(pl, dbuf[s], dbuf[s], nb, st[s], wbuf[s], wbytes, wbytes != 0);
+        if (rc != B200FFT_OK) break;
+        if (!rt::d2h_async(dst, dbuf[s], nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        if (st[i] && !rt::stream_sync(st[i]) && rc == B200FFT_OK) rc = fail(B200FFT_ERR_CUDA, rt::last_error());
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        if (dbuf[i]) rt::dfree(dbuf[i]);
+        if (wbuf[i]) rt::dfree(wbuf[i]);
+        if (st[i]) rt::stream_destroy(st[i]);
+    }
+    return rc;
+}
+
+// Alternative host-slice path (B200FFT_HOST_PIPE=3): a three-stage pipeline over a ring of device buffers, one
+// stream per stage ordered by events.  Measured SLOWER than the two-stream version above in round 1
+// (3.26 s vs 1.86 s per sweep step, profiles/README.md) -- kept for the round-2 investigation, not the default.
+static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
+    static const bool three_stage = [] {
+        const char* e = std::getenv("B200FFT_HOST_PIPE");
+        return e && std::atoi(e) == 3;
     }();
-    uint64_t chunk = std::max<uint64_t>(1, host_chunk_bytes / tbytes);
+    if (!three_stage) return exec_host_impl_2stream(pl, in, out, n_complex);
+    if (!pl) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    if (pl->len == 0 || n_complex == 0) return B200FFT_OK;
+    if (!in || !out) return fail(B200FFT_ERR_INVALID_ARG, "null buffer");
+    if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
+    const uint64_t batch = n_complex / pl->len;
+    const uint64_t tbytes = pl->len * esz;
+    uint64_t chunk = std::max<uint64_t>(1, host_chunk_bytes_cfg() / tbytes);
     if (chunk > batch) chunk = batch;
     const uint64_t nchunks = (batch + chunk - 1) / chunk;
     const int NB = (int)std::min<uint64_t>(4, nchunks);
