@@ -667,14 +667,16 @@ struct Builder {
         while (n % 5 == 0) { n /= 5; ++c; }
         while (n % 7 == 0) { n /= 7; ++d; }
         if (n != 1) return false;
-        // largest radices first (fewest shared-memory passes); odd radices after the powers of two
+        // odd radices FIRST: stage 0 scatters its outputs with a stride of R0 elements, and an odd stride is
+        // free of shared-memory bank conflicts (a radix-16 first stage would be a 16-way conflict); then
+        // the powers of two, largest first (fewest passes)
+        for (uint32_t i = 0; i < d; ++i) radices.push_back(7);
+        for (uint32_t i = 0; i < c; ++i) radices.push_back(5);
+        for (uint32_t i = 0; i < b; ++i) radices.push_back(3);
         while (a >= 4) { radices.push_back(16); a -= 4; }
         if (a == 3) radices.push_back(8);
         if (a == 2) radices.push_back(4);
         if (a == 1) radices.push_back(2);
-        for (uint32_t i = 0; i < d; ++i) radices.push_back(7);
-        for (uint32_t i = 0; i < c; ++i) radices.push_back(5);
-        for (uint32_t i = 0; i < b; ++i) radices.push_back(3);
         return !radices.empty() && radices.size() <= 8;
     }
     template <bool SW>

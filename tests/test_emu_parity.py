@@ -38,8 +38,8 @@ def test_sampled_lens_up_to_1000_and_plan_kinds(planner):
     assert {"Direct", "Bluestein", "Rader", "Smooth"} <= seen
 
 
-@pytest.mark.parametrize("n,desc", [(6, "Smooth{6=2x3}"), (1000, "Smooth{1000=8x5x5x5}"), (343, "Smooth{343=7x7x7}"),
-                                    (1536, "Smooth{1536=16x16x2x3}"), (7, "Smooth{7=7}"), (105, "Smooth{105=7x5x3}")])
+@pytest.mark.parametrize("n,desc", [(6, "Smooth{6=3x2}"), (1000, "Smooth{1000=5x5x5x8}"), (343, "Smooth{343=7x7x7}"),
+                                    (1536, "Smooth{1536=3x16x16x2}"), (7, "Smooth{7=7}"), (105, "Smooth{105=7x5x3}")])
 def test_smooth_plans(planner, n, desc):
     """7-smooth lengths run natively (radix 16/8/4/2/7/5/3 stages), cf. RadixN in src/algorithm/radixn.rs."""
     pl, dtype = planner
