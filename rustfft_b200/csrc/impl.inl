@@ -104,6 +104,7 @@ struct ExecCtx {
     void* work;
     uint64_t batch;
     rt::stream_t stream;
+    int max_streams;  // 0 = plan default; the host-slice pipeline passes 1 (it is PCIe bound and already staged)
 };
 
 }  // namespace b2
@@ -441,7 +442,7 @@ struct Builder {
             C* out = (C*)c.out;
             C* work = (C*)c.work;
             const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
-            const int ns = (int)std::min<uint64_t>((uint64_t)K, nchunks);  // streams actually used
+            const int ns = (int)std::min<uint64_t>((uint64_t)(c.max_streams > 0 ? std::min(c.max_streams, K) : K), nchunks);  // streams used
             rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
             rt::event_t ev_fork = nullptr;
             if (ns > 1) {
@@ -619,7 +620,7 @@ struct Builder {
             const C* in = (const C*)c.in;
             C* out = (C*)c.out;
             const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
-            const int ns = (int)std::min<uint64_t>((uint64_t)K, nchunks);
+            const int ns = (int)std::min<uint64_t>((uint64_t)(c.max_streams > 0 ? std::min(c.max_streams, K) : K), nchunks);
             const uint64_t per = std::min(c.batch, chunk) * M;  // elements of one workspace
             rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
             rt::event_t ev_fork = nullptr;
@@ -911,7 +912,7 @@ static int validate_len(const b200fft_plan* pl, uint64_t n_in, uint64_t n_out, b
 }
 
 static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_out, uint64_t batch, rt::stream_t stream,
-                            void* ws, uint64_t ws_bytes, bool ws_given) {
+                            void* ws, uint64_t ws_bytes, bool ws_given, int max_streams = 0) {
     if (!pl || (!d_in && batch && pl->len) || (!d_out && batch && pl->len)) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
     if (pl->len == 0 || batch == 0) return B200FFT_OK;  // src/fft_helper.rs:16-18
     if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
@@ -928,7 +929,7 @@ static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_ou
             own = true;
         }
     }
-    ExecCtx c{d_in, d_out, work, batch, stream};
+    ExecCtx c{d_in, d_out, work, batch, stream, max_streams};
     const bool ok = pl->exec(c);
     if (own) rt::free_async(work, stream);
     if (!ok) return fail(B200FFT_ERR_CUDA, "kernel launch failed: " + rt::last_error());
@@ -975,7 +976,7 @@ static int exec_host_impl_2stream(const b200fft_plan* pl, const void* in, void* 
         const char* src = (const char*)in + b0 * tbytes;
         char* dst = (char*)out + b0 * tbytes;
         if (!rt::h2d_async(dbuf[s], src, nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
-        rc = exec_device_impl(pl, dbuf[s], dbuf[s], nb, st[s], wbuf[s], wbytes, wbytes != 0);
+        rc = exec_device_impl(pl, dbuf[s], dbuf[s], nb, st[s], wbuf[s], wbytes, wbytes != 0, 1);
         if (rc != B200FFT_OK) break;
         if (!rt::d2h_async(dst, dbuf[s], nb * tbytes, st[s])) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
     }
@@ -990,13 +991,16 @@ static int exec_host_impl_2stream(const b200fft_plan* pl, const void* in, void* 
     return rc;
 }
 
-// Alternative host-slice path (B200FFT_HOST_PIPE=3): a three-stage pipeline over a ring of device buffers, one
-// stream per stage ordered by events.  Measured SLOWER than the two-stream version above in round 1
-// (3.26 s vs 1.86 s per sweep step, profiles/README.md) -- kept for the round-2 investigation, not the default.
+// Host-slice path (default; B200FFT_HOST_PIPE=2 selects the two-stream version above): a three-stage pipeline
+// over a ring of four device buffers -- one stream only copies in, one only computes, one only copies out,
+// ordered per chunk by events -- so both PCIe directions and the SMs are busy at once.  Measured on the round-1
+// box: 47.5 GB/s per direction for one-pass plans = the link's concurrent H2D+D2H limit (47.3 GB/s with plain
+// cudaMemcpyAsync), against 41-44 GB/s for the two-stream version.  Multi-pass plans run their chunks on the
+// single compute stream here (max_streams = 1): their internal two-stream overlap halved the copy rate.
 static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
     static const bool three_stage = [] {
         const char* e = std::getenv("B200FFT_HOST_PIPE");
-        return e && std::atoi(e) == 3;
+        return !(e && std::atoi(e) == 2);
     }();
     if (!three_stage) return exec_host_impl_2stream(pl, in, out, n_complex);
     if (!pl) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
@@ -1035,7 +1039,7 @@ static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uin
         if (idx >= (uint64_t)NB) ok = rt::stream_wait(s_in, ev_out[b]);  // ring slot drained
         ok = ok && rt::h2d_async(dbuf[b], src, nb * tbytes, s_in) && rt::event_record(ev_in[b], s_in) && rt::stream_wait(s_k, ev_in[b]);
         if (!ok) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
-        rc = exec_device_impl(pl, dbuf[b], dbuf[b], nb, s_k, wbuf, wbytes, wbytes != 0);
+        rc = exec_device_impl(pl, dbuf[b], dbuf[b], nb, s_k, wbuf, wbytes, wbytes != 0, 1);
         if (rc != B200FFT_OK) break;
         ok = rt::event_record(ev_k[b], s_k) && rt::stream_wait(s_out, ev_k[b]) && rt::d2h_async(dst, dbuf[b], nb * tbytes, s_out) &&
              rt::event_record(ev_out[b], s_out);
