@@ -294,6 +294,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                         "frac_b2b": round(g2 / hbm, 4)})
         per_size.append(row)
     achieved = step_bytes / (step_ms * 1e-3) / 1e9
+    dom = max(per_size, key=lambda r: r["ms"])  # the size (= kernel pair) the step spends most of its time in
+    dominant = {"kernel": dom["plan"] + " at N=2^%d, batch %d (every launch of the plan, CUDA events around the exec)" % (dom["log2n"], BATCH),
+                "share_of_step": round(dom["ms"] / step_ms, 3), "achieved": dom["gbs"], "frac": dom["frac"], "unit": "GB/s",
+                "algorithmic_bytes_per_exec": int(16 * (1 << dom["log2n"]) * BATCH), "launches_per_exec": plans[dom["log2n"]].launches(BATCH)}
     launches = sum(plans[lg].launches(BATCH) for lg in logs) * args.steps
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -425,9 +429,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "per_size": per_size},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
                          "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "whole step (every launch in it is one of this repo's FFT passes); "
-                                   "dominant = FourStep{1024x1024} passes A+B at N=2^20",
-                         "algorithmic_bytes_per_step": int(step_bytes)},
+                         "kernel": "whole step (every launch in it is one of this repo's FFT passes)",
+                         "algorithmic_bytes_per_step": int(step_bytes), "dominant_kernel": dominant,
+                         "traffic_note": "dram__bytes_read+write summed over the launches of one step, ncu --cache-control none "
+                                         "(profiles/traffic.json)" if traffic else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "other_configs": extras,
         }), flush=True)
     if dist:

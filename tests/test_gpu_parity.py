@@ -164,6 +164,28 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
                 f.process_device(d2, workspace=ws[: nbytes // 2])
 
 
+@pytest.mark.parametrize("env", [
+    {"B200FFT_PIPELINE": "1"},                      # persistent TMA (cp.async.bulk + mbarrier) kernels
+    {"B200FFT_RADIX32": "0"},                       # radix <= 16 geometries
+    {"B200FFT_OVERLAP": "0"},                       # multi-pass chunks on one stream
+    {"B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8"},  # many small chunks over four streams
+    {"B200FFT_HOST_PIPE": "2"},                     # two-stream host-slice path
+], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream"])
+def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
+    import os
+    import subprocess
+    import sys
+
+    from util import ROOT
+
+    e = dict(os.environ)
+    e.update(env)
+    e["PYTHONPATH"] = ROOT + os.pathsep + os.path.join(ROOT, "tests")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variant_check.py")], env=e, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "VARIANT-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_host_pipeline_many_chunks(torch_cuda):
     """Host-slice path with more 64 MiB staging chunks than ring slots (4): 6.x chunks, pageable and pinned."""
     torch = torch_cuda
