@@ -195,7 +195,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_warm = 1 if args.profile else max(args.warmup, 3)
+    n_warm = (0 if args.profile_cold else 1) if args.profile else max(args.warmup, 3)
     for _ in range(n_warm):
         for lg in logs:
             one_size(lg)
@@ -453,10 +453,13 @@ def main():
     ap.add_argument("--e2e-pinned-gib", type=float, default=4.0)
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up, no e2e / cpu legs")
+    ap.add_argument("--profile-cold", action="store_true", help="with --profile: no warm-up sweep at all (launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.profile_cold:
+        args.profile = True
     if args.profile or args.logs:
         args.no_extras = True
     if args.profile:
