@@ -1,202 +1,6 @@
-// libb200fft.so -- CUDA translation unit: the `rt::` layer on the CUDA runtime + every sm_100a kernel
-// instantiation (through impl.inl).  Build: see rustfft_b200/csrc/Makefile
-//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
-#include <cuda_runtime.h>
-
-#include <atomic>
-#include <string>
-
-#include "common.h"
-
-namespace b2 {
-namespace rt {
-
-typedef cudaStream_t stream_t;
-
-static thread_local std::string g_err;
-static bool check(cudaError_t e, const char* what) {
-    if (e == cudaSuccess) return true;
-    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
-    return false;
-}
-static std::string last_error() { return g_err; }
-
-// devices this library can run on: compute capability 10.x (the cubin is sm_100a only)
-static int device_count() {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    int usable = 0;
-    for (int d = 0; d < n; ++d) {
-        int major = 0;
-        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++usable;
-        else break;  // keep device indices dense
-    }
-    return usable;
-}
-static bool set_device(int d) { return check(cudaSetDevice(d), "cudaSetDevice"); }
-static void* dmalloc(size_t bytes) {
-    void* p = nullptr;
-    if (!check(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
-    return p;
-}
-static void dfree(void* p) { cudaFree(p); }
-static bool h2d_sync(void* d, const void* h, size_t n) { return check(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice), "cudaMemcpy H2D"); }
-static bool h2d_async(void* d, const void* h, size_t n, stream_t s) {
-    return check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync H2D");
-}
-static bool d2h_async(void* h, const void* d, size_t n, stream_t s) {
-    return check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync D2H");
-}
-static bool d2d_async(void* dst, const void* src, size_t n, stream_t s) {
-    return check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync D2D");
-}
-static void* malloc_async(size_t bytes, stream_t s) {
-    void* p = nullptr;
-    if (!check(cudaMallocAsync(&p, bytes, s), "cudaMallocAsync")) return nullptr;
-    return p;
-}
-static void free_async(void* p, stream_t s) { cudaFreeAsync(p, s); }
-static stream_t stream_create() {
-    cudaStream_t s = nullptr;
-    if (!check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
-    return s;
-}
-static void stream_destroy(stream_t s) { cudaStreamDestroy(s); }
-static bool stream_sync(stream_t s) { return check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
-typedef cudaEvent_t event_t;
-static event_t event_create() {
-    cudaEvent_t e = nullptr;
-    if (!check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
-    return e;
-}
-static void event_destroy(event_t e) { cudaEventDestroy(e); }
-static bool event_record(event_t e, stream_t s) { return check(cudaEventRecord(e, s), "cudaEventRecord"); }
-static bool stream_wait(stream_t s, event_t e) { return check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
-
-}  // namespace rt
-}  // namespace b2
-
-#include "kernels.h"
-
-namespace b2 {
-namespace rt {
-
-// once per (kernel, device): opt in to > 48 KiB dynamic shared memory, and ask for a shared-memory
-// carveout that fits as many CTAs as registers and threads allow (the driver's default carveout left
-// the 70 KiB tile kernels at 1 CTA/SM in the first round-1 capture)
-template <class KT>
-static bool ensure_configured() {
-    static std::atomic<uint64_t> configured{0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const uint64_t bit = 1ull << (dev & 63);
-    if (configured.load(std::memory_order_acquire) & bit) return true;
-    if (KT::SMEM_BYTES > 48 * 1024 &&
-        !check(cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
-               "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
-        return false;
-    if (KT::SMEM_BYTES > 0) {
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, run_kernel<KT>) == cudaSuccess) {
-            const int regs = ((fa.numRegs + 7) / 8) * 8;
-            int want = 65536 / (regs * KT::NT);
-            if (want > 2048 / KT::NT) want = 2048 / KT::NT;
-            if (want < 1) want = 1;
-            const size_t need = (size_t)want * (KT::SMEM_BYTES + 1024);
-            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-            if (pct > 100) pct = 100;
-            cudaFuncSetAttribute(run_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
-        cudaGetLastError();
-    }
-    configured.fetch_or(bit, std::memory_order_release);
-    return true;
-}
-
-// CTAs of this kernel the whole device holds at once (one "wave"); the planner sizes the L2 chunks of
-// multi-pass plans so that every launch is close to a whole number of waves
-template <class KT>
-static int resident_ctas() {
-    if (!ensure_configured<KT>()) return 0;
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_kernel<KT>, KT::NT, KT::SMEM_BYTES) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return per_sm * sms;
-}
-
-template <class KT>
-static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
-    if (ctas == 0) return true;
-    if (ctas > 0x7fffffffull) {
-        g_err = "grid too large";
-        return false;
-    }
-    if (!ensure_configured<KT>()) return false;
-    run_kernel<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
-}
-
-// kernels with run-time sized dynamic shared memory (<= max_smem bytes, configured once)
-template <class KT>
-static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_bytes, size_t max_smem, stream_t s) {
-    if (ctas == 0) return true;
-    if (ctas > 0x7fffffffull) {
-        g_err = "grid too large";
-        return false;
-    }
-    static std::atomic<uint64_t> configured{0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const uint64_t bit = 1ull << (dev & 63);
-    if (!(configured.load(std::memory_order_acquire) & bit)) {
-        if (!check(cudaFuncSetAttribute(run_kernel_dyn<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
-                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
-            return false;
-        cudaFuncSetAttribute(run_kernel_dyn<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured.fetch_or(bit, std::memory_order_release);
-    }
-    run_kernel_dyn<KT><<<(unsigned)ctas, KT::NT, smem_bytes, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
-}
-
-// persistent pipelined kernels: grid = SMs x resident CTAs (queried once per kernel and device)
-template <class KT>
-static bool launch_pipelined(const typename KT::Params& p, stream_t s) {
-    if (p.n_items == 0) return true;
-    static std::atomic<int> grid_for_dev[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int grid = grid_for_dev[dev & 63].load(std::memory_order_acquire);
-    if (grid == 0) {
-        if (!check(cudaFuncSetAttribute(run_pipelined<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
-                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
-            return false;
-        cudaFuncSetAttribute(run_pipelined<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        int per_sm = 0, sms = 0;
-        if (!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_pipelined<KT>, KT::NT, KT::SMEM_BYTES),
-                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
-            return false;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (per_sm < 1 || sms < 1) {
-            g_err = "pipelined kernel does not fit on an SM";
-            return false;
-        }
-        grid = per_sm * sms;
-        grid_for_dev[dev & 63].store(grid, std::memory_order_release);
-    }
-    const unsigned g = (unsigned)((uint64_t)grid < (uint64_t)p.n_items ? grid : (int)p.n_items);
-    run_pipelined<KT><<<g, KT::NT, KT::SMEM_BYTES, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
-}
-
-}  // namespace rt
-}  // namespace b2
-
+// libb200fft.so -- translation unit 1 of 3: the C ABI (include/b200fft.h), plan object, host-slice pipeline.
+// The kernel instantiations live in b200fft_f32.cu / b200fft_f64.cu so the three compile in parallel.
+// Build: rustfft_b200/csrc/Makefile   (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 ...)
+#include "rt_cuda.h"
+#define B2_PART_CABI 1
 #include "impl.inl"

@@ -5,6 +5,7 @@
 // for FMA hardware, not a restatement of the reference's split-radix code.
 #pragma once
 #include "common.h"
+#include "prime_constants.h"
 
 namespace b2 {
 
@@ -196,6 +197,41 @@ template <typename T> B2_HD void bf32(cx<T> (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = o[i];
 }
 
+// Generic odd-prime butterfly (P = 11, 13, 17, 19, 23, 29, 31): the symmetric form the reference's
+// hard-coded prime butterflies use (src/algorithm/butterflies.rs:339-471 for 5, :545-716 for 7, generated code
+// for 11..31): pair x_j with x_{P-j}, then
+//   X_k, X_{P-k} = (x0 + sum_j cos(2 pi jk/P) (x_j + x_{P-j}))  -/+  i (sum_j sin(2 pi jk/P) (x_j - x_{P-j}))
+// i.e. (P-1)^2/2 real-by-complex multiply-adds, each ONE packed FFMA2.
+template <int P, typename T> B2_HD void bf_prime(cx<T> (&v)[P]) {
+    constexpr int H = (P - 1) / 2;
+    cx<T> a[H], b[H];
+    B2_UNROLL
+    for (int j = 1; j <= H; ++j) {
+        a[j - 1] = v[j] + v[P - j];
+        b[j - 1] = v[j] - v[P - j];
+    }
+    const cx<T> x0 = v[0];
+    cx<T> sum = x0;
+    B2_UNROLL
+    for (int j = 0; j < H; ++j) sum = sum + a[j];
+    B2_UNROLL
+    for (int k = 1; k <= H; ++k) {
+        cx<T> c = x0, s = mk<T>(0, 0);
+        B2_UNROLL
+        for (int j = 1; j <= H; ++j) {
+            const int m = (j * k) % P;
+            const int mm = m <= H ? m : P - m;
+            const T cv = PrimeTw<P, T>::c(mm);
+            const T sv = m <= H ? PrimeTw<P, T>::s(mm) : -PrimeTw<P, T>::s(mm);
+            c = axpy(c, cv, a[j - 1]);
+            s = axpy(s, sv, b[j - 1]);
+        }
+        v[k] = add_mi(c, s);      // c - i s
+        v[P - k] = sub_mi(c, s);  // c + i s
+    }
+    v[0] = sum;
+}
+
 // dispatch on a register array
 template <int R, typename T> struct Bfly;
 template <typename T> struct Bfly<1, T> { static B2_HD void run(cx<T> (&)[1]) {} };
@@ -209,5 +245,12 @@ template <typename T> struct Bfly<7, T> {
 template <typename T> struct Bfly<8, T> { static B2_HD void run(cx<T> (&v)[8]) { bf8(v); } };
 template <typename T> struct Bfly<16, T> { static B2_HD void run(cx<T> (&v)[16]) { bf16(v); } };
 template <typename T> struct Bfly<32, T> { static B2_HD void run(cx<T> (&v)[32]) { bf32(v); } };
+template <typename T> struct Bfly<11, T> { static B2_HD void run(cx<T> (&v)[11]) { bf_prime<11>(v); } };
+template <typename T> struct Bfly<13, T> { static B2_HD void run(cx<T> (&v)[13]) { bf_prime<13>(v); } };
+template <typename T> struct Bfly<17, T> { static B2_HD void run(cx<T> (&v)[17]) { bf_prime<17>(v); } };
+template <typename T> struct Bfly<19, T> { static B2_HD void run(cx<T> (&v)[19]) { bf_prime<19>(v); } };
+template <typename T> struct Bfly<23, T> { static B2_HD void run(cx<T> (&v)[23]) { bf_prime<23>(v); } };
+template <typename T> struct Bfly<29, T> { static B2_HD void run(cx<T> (&v)[29]) { bf_prime<29>(v); } };
+template <typename T> struct Bfly<31, T> { static B2_HD void run(cx<T> (&v)[31]) { bf_prime<31>(v); } };
 
 }  // namespace b2

@@ -6,8 +6,8 @@
 // re-decided for a GPU):
 //   len 0, 1                      -> Identity
 //   2^k <= 16384 (f64: 8192)      -> Direct      one CTA pass, Stockham radix-4/8/16 in registers+smem
-//   larger 2^k (<= 2^20)          -> FourStep    two passes, intermediate kept in L2 by chunking
-//   2^a 3^b 5^c 7^d <= 4096       -> Smooth      one CTA pass, run-time radix list (16/8/4/2/7/5/3)
+//   larger 2^k (<= 2^24)          -> FourStep    two passes, intermediate kept in L2 by chunking
+//   prime factors <= 31, n <= 4096 -> Smooth     one CTA pass, run-time radix list (31..11/7/5/3/16/8/4/2)
 //   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= 256, else over FourStep)
 //   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= 4096)
 #include <cstdio>
@@ -25,11 +25,20 @@
 
 namespace b2 {
 
-static thread_local std::string g_last_error;
-static int fail(int code, const std::string& msg) {
+// (inline: one instance shared by the translation units of the library)
+inline thread_local std::string g_last_error;
+inline int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
+
+// which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
+// harness defines none and gets everything)
+#if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64)
+#define B2_PART_CABI 1
+#define B2_PART_F32 1
+#define B2_PART_F64 1
+#endif
 
 // ---- geometry registry ---------------------------------------------------------------------
 // V = tuning variant: 0 = radix <= 16 stages (16 elements per thread), 1 = radix-32 stages (32 per thread)
@@ -90,12 +99,18 @@ B2_TILE(double, 128, 8, 16, 2, 8, 8)
 B2_TILE(double, 256, 8, 8, 4, 8, 8)
 B2_TILE(double, 512, 8, 8, 8, 8, 8)
 B2_TILE(double, 1024, 8, 4, 2, 8, 8, 8)
+// 2048- and 4096-point tiles: lengths 2^21..2^24 (narrow tiles: 32- / 16-byte runs, the price of a 4096-point
+// row or column having to fit one CTA); the radix-32 geometries are the f32 defaults
+B2_TILE(float, 2048, 32, 4, 2, 32, 32)
+B2_TILE(float, 4096, 32, 2, 4, 32, 32)
+B2_TILE(double, 2048, 8, 2, 4, 8, 8, 8)
+B2_TILE(double, 4096, 8, 1, 8, 8, 8, 8)
 
 // largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
 template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
 static constexpr size_t MAX_SMEM_PER_CTA = 227 * 1024;  // opt-in dynamic shared memory limit of sm_100
 static constexpr uint32_t FUSED_CONV_MAX = 4096;  // largest inner FFT of the fused Bluestein / Rader kernels
-static constexpr uint32_t TILE_MIN = 64, TILE_MAX = 1024;
+static constexpr uint32_t TILE_MIN = 64, TILE_MAX = 4096;
 
 // ---- plan object ----------------------------------------------------------------------------
 struct ExecCtx {
@@ -393,6 +408,8 @@ struct Builder {
             case 256: return make_pass_a<256, SW>(pl, lgN, lg2, f);
             case 512: return make_pass_a<512, SW>(pl, lgN, lg2, f);
             case 1024: return make_pass_a<1024, SW>(pl, lgN, lg2, f);
+            case 2048: return make_pass_a<2048, SW>(pl, lgN, lg2, f);
+            case 4096: return make_pass_a<4096, SW>(pl, lgN, lg2, f);
         }
         return false;
     }
@@ -404,6 +421,8 @@ struct Builder {
             case 256: return make_pass_b<256, SW>(pl, lgN, lg1, tw, f);
             case 512: return make_pass_b<512, SW>(pl, lgN, lg1, tw, f);
             case 1024: return make_pass_b<1024, SW>(pl, lgN, lg1, tw, f);
+            case 2048: return make_pass_b<2048, SW>(pl, lgN, lg1, tw, f);
+            case 4096: return make_pass_b<4096, SW>(pl, lgN, lg1, tw, f);
         }
         return false;
     }
@@ -564,6 +583,8 @@ struct Builder {
             case 256: ok = make_conv_a1<256, SW>(pl, t, f) && make_pass_a<256, false>(pl, t.lgM, t.lg2, plain); break;
             case 512: ok = make_conv_a1<512, SW>(pl, t, f) && make_pass_a<512, false>(pl, t.lgM, t.lg2, plain); break;
             case 1024: ok = make_conv_a1<1024, SW>(pl, t, f) && make_pass_a<1024, false>(pl, t.lgM, t.lg2, plain); break;
+            case 2048: ok = make_conv_a1<2048, SW>(pl, t, f) && make_pass_a<2048, false>(pl, t.lgM, t.lg2, plain); break;
+            case 4096: ok = make_conv_a1<4096, SW>(pl, t, f) && make_pass_a<4096, false>(pl, t.lgM, t.lg2, plain); break;
         }
         if (!ok) return false;
         switch (1u << t.lg2) {
@@ -572,6 +593,8 @@ struct Builder {
             case 256: return make_conv_b<256, SW>(pl, t, f);
             case 512: return make_conv_b<512, SW>(pl, t, f);
             case 1024: return make_conv_b<1024, SW>(pl, t, f);
+            case 2048: return make_conv_b<2048, SW>(pl, t, f);
+            case 4096: return make_conv_b<4096, SW>(pl, t, f);
         }
         return false;
     }
@@ -663,6 +686,9 @@ struct Builder {
     static constexpr uint32_t SMOOTH_MAX = sizeof(T) == 4 ? 4096 : 2048;  // 2 * n * sizeof(C) <= 64 KiB
     static bool smooth_factor(uint64_t n, std::vector<uint32_t>& radices) {
         uint32_t a = 0, b = 0, c = 0, d = 0;
+        // the odd-prime butterflies the reference also hard-codes (src/plan.rs:609-634), largest first
+        for (uint32_t p : {31u, 29u, 23u, 19u, 17u, 13u, 11u})
+            while (n % p == 0) { n /= p; radices.push_back(p); }
         while (n % 2 == 0) { n /= 2; ++a; }
         while (n % 3 == 0) { n /= 3; ++b; }
         while (n % 5 == 0) { n /= 5; ++c; }
@@ -872,9 +898,9 @@ struct Builder {
             else if (n <= (uint64_t)TILE_MAX * TILE_MAX)
                 ok = make_four_step(pl, hm::ilog2(n));
             else
-                return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^20 are not planned by this build");
+                return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^24 are not planned by this build");
         } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
-            ok = make_smooth(pl, radices);  // 2^a 3^b 5^c 7^d
+            ok = make_smooth(pl, radices);  // every prime factor <= 31
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {
@@ -887,13 +913,27 @@ struct Builder {
                 ok = make_big_conv(pl, M, false);
             else
                 return fail(B200FFT_ERR_UNSUPPORTED,
-                            "non-power-of-two lengths above 2^19 are not planned by this build");
+                            "non-power-of-two lengths above 2^23 are not planned by this build");
         }
         if (!ok) return fail(B200FFT_ERR_CUDA, "plan construction failed: " + rt::last_error());
         return B200FFT_OK;
     }
 };
 
+// per-precision entry points of the planner, one per translation unit
+int build_plan_f32(b200fft_plan& pl);
+int build_plan_f64(b200fft_plan& pl);
+#if defined(B2_PART_F32)
+int build_plan_f32(b200fft_plan& pl) { return Builder<float>::build(pl); }
+#endif
+#if defined(B2_PART_F64)
+int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
+#endif
+
+}  // namespace b2
+
+#if defined(B2_PART_CABI)
+namespace b2 {
 static int validate_len(const b200fft_plan* pl, uint64_t n_in, uint64_t n_out, bool two) {
     // src/common.rs:13-104 (messages kept verbatim; the Rust shim panics with them)
     const uint64_t len = pl->len;
@@ -1084,7 +1124,7 @@ int b200fft_plan_create(b200fft_plan** out, uint64_t len, int direction, int pre
     pl->direction = direction;
     pl->precision = precision;
     pl->device = device;
-    const int rc = precision == B200FFT_F32 ? b2::Builder<float>::build(*pl) : b2::Builder<double>::build(*pl);
+    const int rc = precision == B200FFT_F32 ? b2::build_plan_f32(*pl) : b2::build_plan_f64(*pl);
     if (rc != B200FFT_OK) return rc;
     *out = pl.release();
     return B200FFT_OK;
@@ -1141,3 +1181,4 @@ const char* b200fft_last_error(void) { return b2::g_last_error.c_str(); }
 const char* b200fft_version(void) { return "b200fft 0.1 sm_100a"; }
 
 }  // extern "C"
+#endif  // B2_PART_CABI

@@ -418,10 +418,10 @@ struct RaderKernel {
 };
 
 // ------------------------------------------------------------------------------------------
-// SmoothKernel: one-pass Stockham FFT for 7-smooth lengths n = 2^a 3^b 5^c 7^d that have no compiled
-// geometry (n <= SMOOTH_MAX).  The radix list is run-time data (the host planner factors n into
-// stages of radix 16/8/4/2/3/5/7 -- the reference's RadixN does the same with 2..7 over a butterfly base,
-// src/algorithm/radixn.rs:54-155, src/plan.rs:508-607); each stage is one pass over a ping-pong pair of
+// SmoothKernel: one-pass Stockham FFT for lengths whose prime factors are all <= 31 and that have no compiled
+// geometry (n <= SMOOTH_MAX).  The radix list is run-time data (the host planner factors n into stages of
+// radix 31..11 / 7 / 5 / 3 / 16 / 8 / 4 / 2 -- the reference's RadixN does the same with 2..7 over a butterfly
+// base taken from its hard-coded set 2..32, src/algorithm/radixn.rs:54-155, src/plan.rs:508-634); each stage is one pass over a ping-pong pair of
 // shared-memory buffers, the first stage reads global memory and the last one writes it, both coalesced
 // and in natural order (same index algebra as engine.h).  Slower per element than the compiled
 // power-of-two geometries (no cross-stage register reuse, generic index arithmetic) but one pass over
@@ -501,6 +501,13 @@ struct SmoothKernel {
             case 7: stage<7>(p, bid, tid, P, smem); break;
             case 8: stage<8>(p, bid, tid, P, smem); break;
             case 16: stage<16>(p, bid, tid, P, smem); break;
+            case 11: stage<11>(p, bid, tid, P, smem); break;
+            case 13: stage<13>(p, bid, tid, P, smem); break;
+            case 17: stage<17>(p, bid, tid, P, smem); break;
+            case 19: stage<19>(p, bid, tid, P, smem); break;
+            case 23: stage<23>(p, bid, tid, P, smem); break;
+            case 29: stage<29>(p, bid, tid, P, smem); break;
+            case 31: stage<31>(p, bid, tid, P, smem); break;
             default: break;
         }
     }

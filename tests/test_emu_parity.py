@@ -39,9 +39,12 @@ def test_sampled_lens_up_to_1000_and_plan_kinds(planner):
 
 
 @pytest.mark.parametrize("n,desc", [(6, "Smooth{6=3x2}"), (1000, "Smooth{1000=5x5x5x8}"), (343, "Smooth{343=7x7x7}"),
-                                    (1536, "Smooth{1536=3x16x16x2}"), (7, "Smooth{7=7}"), (105, "Smooth{105=7x5x3}")])
+                                    (1536, "Smooth{1536=3x16x16x2}"), (7, "Smooth{7=7}"), (105, "Smooth{105=7x5x3}"),
+                                    (143, "Smooth{143=13x11}"), (961, "Smooth{961=31x31}"), (31, "Smooth{31=31}"),
+                                    (1196, "Smooth{1196=23x13x4}"), (1131, "Smooth{1131=29x13x3}"), (323, "Smooth{323=19x17}")])
 def test_smooth_plans(planner, n, desc):
-    """7-smooth lengths run natively (radix 16/8/4/2/7/5/3 stages), cf. RadixN in src/algorithm/radixn.rs."""
+    """Lengths whose prime factors are <= 31 run natively (run-time radix list; odd primes 11..31 use the
+    symmetric prime butterfly), cf. RadixN + the hard-coded butterflies of src/algorithm/butterflies.rs."""
     pl, dtype = planner
     f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=5)
     assert f.describe() == desc
@@ -120,9 +123,21 @@ def test_error_behaviour_and_cache(planner):
 def test_unsupported_lengths_fail_loudly(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     with pytest.raises(rb.FftError, match="not planned by this build"):
-        pl.plan_fft_forward(1 << 21)
+        pl.plan_fft_forward(1 << 25)
     with pytest.raises(rb.FftError, match="not planned by this build"):
-        pl.plan_fft_forward((1 << 19) + 1)
+        pl.plan_fft_forward((1 << 23) + 1)
+
+
+def test_four_step_beyond_2_20(lib):
+    """2^21 and 2^22 through the 2048-point tiles (up to 2^24 = 4096 x 4096 on the GPU suite)."""
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    for n, desc in [(1 << 21, "FourStep{1024x2048}"), (1 << 22, "FourStep{2048x2048}")]:
+        f = pl.plan_fft_forward(n)
+        assert f.describe() == desc
+        x = signal(n, np.complex64, seed=21)
+        y = x.copy()
+        f.process(y)
+        assert rel_l2(y, truth(x, n, False)) <= 4 * 5.96e-8 * np.log2(n)
 
 
 def test_linearity_roundtrip_parseval(planner):

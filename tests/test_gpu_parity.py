@@ -120,7 +120,23 @@ def test_config4_prime_65537_batch_512(torch_cuda):
         assert rel_l2(y[b * n:(b + 1) * n], ref) <= max(strict_bound(n, np.complex64), 2 * rel_l2(want, ref))
 
 
-@pytest.mark.parametrize("n", [2049, 4099, 10007, 44100, 112501, 300000])
+@pytest.mark.parametrize("lg", [21, 22, 23, 24])
+def test_power_of_two_up_to_2_24(planner, lg):
+    """Beyond the BASELINE sweep: 2048/4096-point tiles (the reference benches up to 4 194 304,
+    benches/bench_compare_scalar_sse_avx.rs:123-124)."""
+    pl, dtype = planner
+    n = 1 << lg
+    f = pl.plan_fft_forward(n)
+    assert f.describe().startswith("FourStep{")
+    x = signal(2 * n, dtype, seed=lg)
+    y = x.copy()
+    f.process(y)
+    assert rel_l2(y, truth(x, n, False)) <= strict_bound(n, dtype)
+    pl.plan_fft_inverse(n).process(y)
+    assert rel_l2(y / n, x) <= 2 * strict_bound(n, dtype)
+
+
+@pytest.mark.parametrize("n", [2049, 4099, 10007, 44100, 112501, 300000, 1000003])
 def test_large_non_power_of_two(planner, n):
     """Bluestein over a four-step inner FFT (beyond the reference's accuracy test range, which stops at
     1000; 112501 is one of its 32-bit-overflow Rader primes, raders_algorithm.rs:311-322)."""
@@ -129,12 +145,13 @@ def test_large_non_power_of_two(planner, n):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
-@pytest.mark.parametrize("n", [360, 1000, 1200, 1536, 2000, 2401, 3600, 4000])
+@pytest.mark.parametrize("n", [360, 1000, 1200, 1536, 2000, 2401, 3600, 4000, 143, 961, 1196, 1131, 3683])
 def test_smooth_lengths_native(planner, n):
-    """2^a 3^b 5^c 7^d: one-pass run-time-radix kernel (the reference: RadixN / MixedRadix, plan.rs:508-607)."""
+    """Prime factors <= 31: one-pass run-time-radix kernel (the reference: RadixN / MixedRadix / butterflies
+    2..32, plan.rs:508-634).  3683 = 29 * 127 has a larger factor and goes through Bluestein."""
     pl, dtype = planner
     f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=300)
-    if n <= 2048 or dtype == np.complex64:
+    if n != 3683 and (n <= 2048 or dtype == np.complex64):
         assert f.describe().startswith("Smooth{")
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=3)
 
