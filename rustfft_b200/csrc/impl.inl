@@ -718,6 +718,8 @@ struct Builder {
             const uint32_t R = radices[s];
             base.radix[s] = R;
             base.tw_off[s] = (uint32_t)tw.size();
+            base.div_t[s] = make_fastdiv(n / R);
+            base.div_p[s] = make_fastdiv(p);
             if (s >= 1)
                 for (uint32_t r = 1; r < R; ++r)
                     for (uint32_t k = 0; k < p; ++k) tw.push_back(hm::twiddle<T>((uint64_t)k * r, (uint64_t)p * R));

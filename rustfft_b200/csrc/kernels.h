@@ -427,6 +427,36 @@ struct RaderKernel {
 // power-of-two geometries (no cross-stage register reuse, generic index arithmetic) but one pass over
 // HBM and no padding to a power of two -- against Bluestein's two FFTs of 2-4x the length.
 // ------------------------------------------------------------------------------------------
+// unsigned division by a run-time constant through a precomputed reciprocal (the stage geometry of the
+// SmoothKernel is run-time data; plain `/` and `%` cost ~20 instructions each)
+struct FastDiv {
+    uint32_t d, mul, shift;  // q = umulhi(n, mul) >> shift   (n < 2^31)
+    B2_HD uint32_t div(uint32_t n) const {
+        if (d == 1) return n;
+#if defined(__CUDA_ARCH__)
+        return __umulhi(n, mul) >> shift;
+#else
+        return (uint32_t)(((uint64_t)n * mul) >> 32) >> shift;
+#endif
+    }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0, 0};
+    if (d <= 1) return f;
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;  // ceil(log2 d)
+    // round-up method, exact for n < 2^31
+    const uint64_t m = ((1ull << (32 + l)) + d - 1) / d;
+    if (m < (1ull << 32)) {
+        f.mul = (uint32_t)m;
+        f.shift = l;
+    } else {  // m needs 33 bits: use l-1 (still exact for n < 2^31 because d > 2^(l-1))
+        f.mul = (uint32_t)(((1ull << (32 + l - 1)) + d - 1) / d);
+        f.shift = l - 1;
+    }
+    return f;
+}
+
 template <typename T, bool SWAP>
 struct SmoothKernel {
     using T_ = T;
@@ -443,24 +473,25 @@ struct SmoothKernel {
         uint32_t n, n_stages, f_per_cta, smem_bytes;
         uint32_t radix[MAX_STAGES];
         uint32_t tw_off[MAX_STAGES];
+        FastDiv div_t[MAX_STAGES];  // by T_s = n / radix[s]
+        FastDiv div_p[MAX_STAGES];  // by p_s = product of the radices before s
     };
     struct Regs {};
 
     template <int R>
     static B2_HD void stage(const Params& p, uint32_t bid, int tid, int s, cx<T>* smem) {
         const uint32_t n = p.n, F = p.f_per_cta;
-        uint32_t pp = 1;  // product of the radices before stage s
-        for (int i = 0; i < s; ++i) pp *= p.radix[i];
-        const uint32_t T_s = n / R;  // butterflies per transform
+        const uint32_t pp = p.div_p[s].d;  // product of the radices before stage s
+        const uint32_t T_s = p.div_t[s].d;  // butterflies per transform = n / R
         const bool first = (s == 0), last = (s == (int)p.n_stages - 1);
         const cx<T>* src_buf = smem + (size_t)((s + 1) & 1) * F * n;  // stage s-1 wrote buffer (s-1)&1
         cx<T>* dst_buf = smem + (size_t)(s & 1) * F * n;
         const cx<T>* tws = p.tw + p.tw_off[s];
         for (uint32_t b = (uint32_t)tid; b < F * T_s; b += NT) {
-            const uint32_t f = b / T_s, i = b - f * T_s;
+            const uint32_t f = p.div_t[s].div(b), i = b - f * T_s;
             const uint64_t g = (uint64_t)bid * F + f;
             if (g >= p.n_fft) continue;
-            const uint32_t k = i % pp;
+            const uint32_t k = i - p.div_p[s].div(i) * pp;
             cx<T> a[R];
             if (first) {
                 const cx<T>* src = p.in + g * (uint64_t)n + i;
