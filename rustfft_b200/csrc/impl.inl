@@ -230,6 +230,38 @@ static int overlap_streams() {
     return v;
 }
 
+// B200FFT_FLOW=0: two-pass plans run as one launch pair per L2 chunk (the round-1 path).  Default: the single-launch
+// dataflow kernel (kernels.h, run_flow).  B200FFT_FLOW_LOOKAHEAD = tickets pass A runs ahead of pass B (default 500),
+// B200FFT_FLOW_W forces the number of ring slots (power of two >= 2).
+static bool use_flow() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_FLOW");
+        return !(e && std::atoi(e) == 0);
+    }();
+    return v;
+}
+static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform) {
+    static const uint32_t forced = [] {
+        const char* e = std::getenv("B200FFT_FLOW_W");
+        return e ? (uint32_t)std::atoi(e) : 0u;
+    }();
+    static const uint32_t look = [] {
+        const char* e = std::getenv("B200FFT_FLOW_LOOKAHEAD");
+        const int k = e ? std::atoi(e) : 500;
+        return (uint32_t)(k < 1 ? 1 : k);
+    }();
+    uint32_t W = 4;
+    if (forced >= 2) {
+        W = 2;
+        while (W < forced) W <<= 1;
+        return W;
+    }
+    while ((uint64_t)(W - 2) * per_round < look && W < 1024) W <<= 1;
+    // the ring must stay L2 resident: at most 64 MiB, but never fewer than two slots
+    while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W >>= 1;
+    return W;
+}
+
 // B200FFT_RADIX32=0 disables the radix-32 geometries (A/B measurements)
 static bool use_radix32() {
     static bool v = [] {
@@ -434,12 +466,92 @@ struct Builder {
             for (uint64_t n2 = 0; n2 < N2; ++n2) t[(size_t)(k1 * N2 + n2)] = hm::twiddle<T>(k1 * n2, N);
         return upload(pl, t);
     }
+    // ---- single-launch dataflow variant (kernels.h: run_flow) ----
+    template <int L> struct FlowGeo { using type = typename TileGeo<T, L, HasV1<T, L>::tile ? 1 : 0>::type; };
+    typedef std::function<bool(const C* in, C* out, void* work, uint64_t batch, rt::stream_t)> FlowFn;
+    template <int L1, int L2, bool SW>
+    static bool make_flow_t(b200fft_plan& pl, uint32_t lgN, const C* full_tw, FlowFn& fn, uint32_t& W_out) {
+        using GA = typename FlowGeo<L1>::type;
+        using GB = typename FlowGeo<L2>::type;
+        using KA = FftKernel<GA, FF, FF, LoadCols<T, SW>, StoreColsRing<T>>;
+        using KB = FftKernel<GB, JF, FF, LoadRowsTwRing<T>, StoreTransposed<T, SW>>;
+        using FK = FlowKernel<KA, KB>;
+        const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2);
+        const C* twa = upload(pl, stage_twiddles<GA>());
+        const C* twb = upload(pl, stage_twiddles<GB>());
+        if (!twa || !twb) return false;
+        if (rt::flow_grid<KA, KB>() <= 0) return false;
+        const uint32_t TA = (uint32_t)L2 / GA::F, TB = (uint32_t)L1 / GB::F;
+        const uint64_t N = 1ull << lgN;
+        const uint32_t W = flow_ring_slots(TA + TB, N * sizeof(C));
+        W_out = W;
+        const uint64_t ctl_bytes = flow_ctl_bytes(W);
+        fn = [=](const C* in, C* out, void* work, uint64_t batch, rt::stream_t s) {
+            // 2^24 transforms per launch keeps the ticket count inside 32 bits for every geometry
+            const uint64_t seg = 1ull << 24;
+            for (uint64_t b0 = 0; b0 < batch; b0 += seg) {
+                const uint64_t nb = std::min(seg, batch - b0);
+                typename FK::Params p;
+                C* ring = (C*)((char*)work + ctl_bytes);
+                p.a.load = LoadCols<T, SW>{in + b0 * N, lgN, lg2};
+                p.a.store = StoreColsRing<T>{ring, lgN, lg2, W - 1};
+                p.a.tw = twa;
+                p.a.n_fft = nb << lg2;
+                p.b.load = LoadRowsTwRing<T>{ring, full_tw, (uint32_t)L2, lg1, lgN, W - 1};
+                p.b.store = StoreTransposed<T, SW>{out + b0 * N, lgN, lg1};
+                p.b.tw = twb;
+                p.b.n_fft = nb << lg1;
+                p.ctl = (uint32_t*)work;
+                if (!make_flow_sched(p.sched, nb, TA, TB, W)) {
+                    rt::g_err = "dataflow schedule overflow";
+                    return false;
+                }
+                if (!rt::launch_flow<KA, KB>(p, ctl_bytes, s)) return false;
+            }
+            return true;
+        };
+        return true;
+    }
+    template <int L1>
+    static bool make_flow_l1(b200fft_plan& pl, uint32_t L2, uint32_t lgN, const C* tw, FlowFn& fn, uint32_t& W) {
+        const bool sw = pl.direction != 0;
+        if (L2 == (uint32_t)L1) return sw ? make_flow_t<L1, L1, true>(pl, lgN, tw, fn, W) : make_flow_t<L1, L1, false>(pl, lgN, tw, fn, W);
+        if constexpr (2 * L1 <= (int)TILE_MAX) {
+            if (L2 == 2u * L1)
+                return sw ? make_flow_t<L1, 2 * L1, true>(pl, lgN, tw, fn, W) : make_flow_t<L1, 2 * L1, false>(pl, lgN, tw, fn, W);
+        }
+        return false;
+    }
+    static bool make_flow_rt(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const C* tw, FlowFn& fn, uint32_t& W) {
+        switch (L1) {
+            case 128: return make_flow_l1<128>(pl, L2, lgN, tw, fn, W);
+            case 256: return make_flow_l1<256>(pl, L2, lgN, tw, fn, W);
+            case 512: return make_flow_l1<512>(pl, L2, lgN, tw, fn, W);
+            case 1024: return make_flow_l1<1024>(pl, L2, lgN, tw, fn, W);
+            case 2048: return make_flow_l1<2048>(pl, L2, lgN, tw, fn, W);
+            case 4096: return make_flow_l1<4096>(pl, L2, lgN, tw, fn, W);
+        }
+        return false;
+    }
     static bool make_four_step(b200fft_plan& pl, uint32_t lgN) {
         const uint32_t lg1 = lgN / 2, lg2 = lgN - lg1;  // N1 <= N2
         const uint32_t N1 = 1u << lg1, N2 = 1u << lg2;
         if (N1 < TILE_MIN || N2 > TILE_MAX) return false;
         const C* full_tw = make_full_twiddles(pl, lg1, lg2);
         if (!full_tw) return false;
+        if (use_flow() && N1 >= 128) {
+            FlowFn fn;
+            uint32_t W = 0;
+            if (!make_flow_rt(pl, N1, N2, lgN, full_tw, fn, W)) return false;
+            const uint64_t Nn = 1ull << lgN;
+            const uint64_t wbytes = flow_ctl_bytes(W) + (uint64_t)W * Nn * sizeof(C);
+            pl.work_bytes = [=](uint64_t) { return wbytes; };
+            pl.launches = [=](uint64_t batch) { return (batch + (1ull << 24) - 1) >> 24; };
+            pl.exec = [=](const ExecCtx& c) { return fn((const C*)c.in, (C*)c.out, c.work, c.batch, c.stream); };
+            pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + ",flow,ring=" + std::to_string(W) + "}";
+            pl.chunk = W;
+            return true;
+        }
         PassFns fns;
         const bool sw = pl.direction != 0;
         const bool ok_a = sw ? make_pass_a_rt<true>(pl, N1, lgN, lg2, fns) : make_pass_a_rt<false>(pl, N1, lgN, lg2, fns);

@@ -134,6 +134,41 @@ struct StoreTransposed {
     }
 };
 
+// ---- ring-addressed workspace functors of the single-launch dataflow four-step (run_flow below) ----
+// The intermediate of transform b lives in slot (b & ring_mask) of a small ring of N-element slots that
+// stays L2 resident; everything else is as in StoreCols / LoadRowsTw.
+template <typename T>
+struct StoreColsRing {
+    cx<T>* out;
+    uint32_t lgN, lg2, ring_mask;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t b = (g >> lg2) & ring_mask, c = g & ((1ull << lg2) - 1);
+        return St{out + (b << lgN) + c, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) s.p[(uint32_t)e << lg2] = v;  // plain write-back store: pass B re-reads it from L2
+    }
+};
+template <typename T>
+struct LoadRowsTwRing {
+    const cx<T>* in;
+    const cx<T>* tw;  // [N1][N2]
+    uint32_t len;     // N2
+    uint32_t lg1;     // log2 N1
+    uint32_t lgN, ring_mask;
+    struct St { const cx<T>* p; const cx<T>* t; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint64_t k1 = g & ((1ull << lg1) - 1), b = (g >> lg1) & ring_mask;
+        return St{in + (b << lgN) + k1 * (uint64_t)len, tw + k1 * (uint64_t)len, ok};
+    }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        // ld.global.cs is a coherent (weak) load: ordered after the acquire of the slot's ready counter
+        return cmul(ld_cs(s.p + e), ldg_stream(s.t + e));
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Functors of the large convolution plans (Rader / Bluestein with an inner FFT of M = N1*N2 > one
 // CTA): the same two four-step passes, with the algorithm's gather / chirp / pointwise / scatter
@@ -627,6 +662,78 @@ struct PipeKernel {
 };
 
 // ------------------------------------------------------------------------------------------
+// Single-launch dataflow four-step.
+//
+// One persistent grid (one CTA per resident slot) executes BOTH passes of every transform of a batch.
+// Work is a single ordered list of tickets handed out by an atomic counter: round r holds the TA tiles of
+// pass A of transform r and the TB tiles of pass B of transform r - D, interleaved, so at any moment the
+// device is reading new input from HBM (A tiles) and writing finished output to HBM (B tiles) while the
+// intermediate lives in a ring of W = D + 2 (power of two) N-element slots that never leaves L2.
+//   B(t) may start when all TA tiles of A(t) have been stored     (ready[slot] >= (gen + 1) * TA)
+//   A(t) may start when all TB tiles of B(t - W) have been read   (freed[slot] >= gen * TB)
+// with slot = t mod W, gen = t / W; both counters only grow.  A dependency always points to a SMALLER ticket,
+// and a CTA owns a ticket only while it runs, so the smallest unfinished ticket can always proceed: no
+// deadlock whatever the number of co-resident CTAs.  Compared with one launch pair per L2 chunk (the path
+// it replaces, ~1000 launches per exec at N = 2^20) there are no per-launch ramps and tails, no host-side
+// chunk loop, and reads and writes of HBM are mixed at tile granularity instead of per launch.
+// ------------------------------------------------------------------------------------------
+struct FlowSched {
+    uint32_t batch, TA, TB, D, ring_mask, per_round, m, a_big, n_rounds, total;
+    B2_HD void decode(uint32_t ticket, int& kind, uint32_t& t, uint32_t& tile, bool& valid) const {
+        const uint32_t r = ticket / per_round, i = ticket - r * per_round;
+        const uint32_t period = m + 1, k = i / period, j = i - k * period;
+        const bool big = j < m;
+        tile = big ? k * m + j : k;
+        if (big == (a_big != 0)) {
+            kind = 0;
+            t = r;
+            valid = r < batch;
+        } else {
+            kind = 1;
+            t = r - D;
+            valid = r >= D && t < batch;
+        }
+    }
+};
+// returns false when the ticket count would overflow 32 bits (the caller falls back to the chunked path)
+inline bool make_flow_sched(FlowSched& s, uint64_t batch, uint32_t TA, uint32_t TB, uint32_t W) {
+    s.TA = TA;
+    s.TB = TB;
+    s.ring_mask = W - 1;
+    uint32_t D = W > 2 ? W - 2 : 1;
+    if ((uint64_t)D > batch) D = (uint32_t)batch;
+    if (D < 1) D = 1;
+    s.D = D;
+    s.per_round = TA + TB;
+    s.a_big = TA >= TB ? 1u : 0u;
+    s.m = s.a_big ? TA / TB : TB / TA;
+    const uint64_t rounds = batch + D, total = rounds * s.per_round;
+    if (batch >= (1ull << 31) || total >= (1ull << 31)) return false;
+    s.batch = (uint32_t)batch;
+    s.n_rounds = (uint32_t)rounds;
+    s.total = (uint32_t)total;
+    return true;
+}
+// control block at the head of the workspace (zeroed before every launch): [0] ticket, [1] error flag,
+// [32 .. 32+W) ready counters, [32+W .. 32+2W) freed counters
+static constexpr uint32_t FLOW_CTL_HEAD = 32;
+inline uint64_t flow_ctl_bytes(uint32_t W) { return ((uint64_t)(FLOW_CTL_HEAD + 2 * W) * 4 + 255) / 256 * 256; }
+
+template <class KA, class KB>
+struct FlowKernel {
+    using T = typename KA::T;
+    static constexpr int NT = KA::NT > KB::NT ? KA::NT : KB::NT;
+    static constexpr int MIN_BLOCKS = KA::MIN_BLOCKS < KB::MIN_BLOCKS ? KA::MIN_BLOCKS : KB::MIN_BLOCKS;
+    static constexpr size_t SMEM_BYTES = KA::SMEM_BYTES > KB::SMEM_BYTES ? KA::SMEM_BYTES : KB::SMEM_BYTES;
+    struct Params {
+        typename KA::Params a;
+        typename KB::Params b;
+        FlowSched sched;
+        uint32_t* ctl;
+    };
+};
+
+// ------------------------------------------------------------------------------------------
 // Device entry point shared by all kernels.
 // ------------------------------------------------------------------------------------------
 template <class KT, int P>
@@ -658,6 +765,86 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T_>*>(smem_raw));
+}
+
+// phases of one tile inside a CTA that may have more threads than the tile's kernel uses
+template <class KT, int NTC, int P>
+struct FlowPhases {
+    static B2_D void run(const typename KT::Params& p, uint32_t bid, int tid, typename KT::Regs& r, cx<typename KT::T>* smem) {
+        if (NTC == KT::NT || tid < KT::NT) KT::template phase<P>(p, bid, tid, r, smem);
+        if constexpr (P + 1 < KT::NPHASE) {
+            __syncthreads();
+            FlowPhases<KT, NTC, P + 1>::run(p, bid, tid, r, smem);
+        }
+    }
+};
+B2_D uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// thread 0 spins until *ctr >= target (bounded: a scheduling bug sets the error flag instead of hanging the GPU)
+B2_D void flow_wait(uint32_t* ctl, const uint32_t* ctr, uint32_t target, int tid) {
+    if (tid == 0) {
+        uint32_t spins = 0;
+        while (ld_acquire_u32(ctr) < target) {
+            __nanosleep(spins < 64 ? 32 : 256);
+            if (++spins > (1u << 22) || (spins > 4096 && ld_acquire_u32(ctl + 1) != 0)) {
+                atomicExch(ctl + 1, 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <class KA, class KB>
+__global__ void __launch_bounds__(FlowKernel<KA, KB>::NT, FlowKernel<KA, KB>::MIN_BLOCKS)
+run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
+    using FK = FlowKernel<KA, KB>;
+    using C = cx<typename FK::T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_ticket[2];
+    C* smem = reinterpret_cast<C*>(smem_raw);
+    const int tid = (int)threadIdx.x;
+    const FlowSched& sc = p.sched;
+    uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
+    uint32_t* freed = ready + (sc.ring_mask + 1);
+    if (tid == 0) s_ticket[0] = atomicAdd(p.ctl, 1u);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t ticket = s_ticket[it & 1u];
+        if (ticket >= sc.total) break;
+        // next ticket is fetched while this tile runs (its latency never sits between two tiles)
+        if (tid == 0) s_ticket[(it + 1u) & 1u] = atomicAdd(p.ctl, 1u);
+        int kind;
+        uint32_t t, tile;
+        bool valid;
+        sc.decode(ticket, kind, t, tile, valid);
+        if (valid) {
+            const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+            if (kind == 0) {
+                if (gen > 0) flow_wait(p.ctl, freed + slot, gen * sc.TB, tid);
+                typename KA::Regs r;
+                FlowPhases<KA, FK::NT, 0>::run(p.a, t * sc.TA + tile, tid, r, smem);
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    atomicAdd(ready + slot, 1u);
+                }
+            } else {
+                flow_wait(p.ctl, ready + slot, (gen + 1u) * sc.TA, tid);
+                typename KB::Regs r;
+                FlowPhases<KB, FK::NT, 0>::run(p.b, t * sc.TB + tile, tid, r, smem);
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    atomicAdd(freed + slot, 1u);
+                }
+            }
+        }
+        __syncthreads();  // shared memory and s_ticket are reused by the next tile
+    }
 }
 
 template <class KT>

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 
@@ -53,6 +54,7 @@ static bool d2h_async(void* h, const void* d, size_t n, stream_t s) {
 static bool d2d_async(void* dst, const void* src, size_t n, stream_t s) {
     return check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync D2D");
 }
+static bool memset_async(void* d, int v, size_t n, stream_t s) { return check(cudaMemsetAsync(d, v, n, s), "cudaMemsetAsync"); }
 static void* malloc_async(size_t bytes, stream_t s) {
     void* p = nullptr;
     if (!check(cudaMallocAsync(&p, bytes, s), "cudaMallocAsync")) return nullptr;
@@ -193,6 +195,58 @@ static bool launch_pipelined(const typename KT::Params& p, stream_t s) {
     }
     const unsigned g = (unsigned)((uint64_t)grid < (uint64_t)p.n_items ? grid : (int)p.n_items);
     run_pipelined<KT><<<g, KT::NT, KT::SMEM_BYTES, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
+// single-launch dataflow four-step: persistent grid = resident CTAs (queried once per kernel and device);
+// the control block is zeroed on the stream right before the launch (both are graph-capturable)
+template <class KA, class KB>
+static int flow_grid() {
+    using FK = FlowKernel<KA, KB>;
+    static std::atomic<int> grid_for_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int grid = grid_for_dev[dev & 63].load(std::memory_order_acquire);
+    if (grid == 0) {
+        if (FK::SMEM_BYTES > 48 * 1024 &&
+            !check(cudaFuncSetAttribute(run_flow<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FK::SMEM_BYTES),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return 0;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, run_flow<KA, KB>) == cudaSuccess) {
+            const int regs = ((fa.numRegs + 7) / 8) * 8;
+            int want = 65536 / (regs * FK::NT);
+            if (want > 2048 / FK::NT) want = 2048 / FK::NT;
+            if (want < 1) want = 1;
+            const size_t need = (size_t)want * (FK::SMEM_BYTES + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            cudaFuncSetAttribute(run_flow<KA, KB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        cudaGetLastError();
+        int per_sm = 0, sms = 0;
+        if (!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_flow<KA, KB>, FK::NT, FK::SMEM_BYTES),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+            return 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1 || sms < 1) {
+            g_err = "dataflow kernel does not fit on an SM";
+            return 0;
+        }
+        grid = per_sm * sms;
+        grid_for_dev[dev & 63].store(grid, std::memory_order_release);
+    }
+    return grid;
+}
+template <class KA, class KB>
+static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t ctl_bytes, stream_t s) {
+    using FK = FlowKernel<KA, KB>;
+    if (p.sched.total == 0) return true;
+    const int grid = flow_grid<KA, KB>();
+    if (grid <= 0) return false;
+    if (!memset_async(p.ctl, 0, ctl_bytes, s)) return false;
+    const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)grid, (uint64_t)p.sched.total);
+    run_flow<KA, KB><<<g, FK::NT, FK::SMEM_BYTES, s>>>(p);
     return check(cudaGetLastError(), "kernel launch");
 }
 

@@ -27,6 +27,7 @@ static bool h2d_sync(void* d, const void* h, size_t n) { std::memcpy(d, h, n); r
 static bool h2d_async(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); return true; }
 static bool d2h_async(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); return true; }
 static bool d2d_async(void* dst, const void* src, size_t n, stream_t) { std::memmove(dst, src, n); return true; }
+static bool memset_async(void* d, int v, size_t n, stream_t) { std::memset(d, v, n); return true; }
 static void* malloc_async(size_t n, stream_t) { return std::malloc(n ? n : 1); }
 static void free_async(void* p, stream_t) { std::free(p); }
 static stream_t stream_create() { return (stream_t)1; }
@@ -95,6 +96,49 @@ static bool launch_pipelined(const typename KT::Params& p, stream_t) {
         std::memcpy(buf.data(), KT::fetch_src(p, item), KT::fetch_bytes(p, item));
         EmuPhases<KT, 0>::run(p, item, regs, buf.data());
     }
+    return true;
+}
+
+// single-launch dataflow four-step: ONE emulated CTA takes the tickets in order, so every dependency (which always
+// points to a smaller ticket) must already be satisfied when its tile starts -- checked here; the counters are
+// kept exactly as the device kernel keeps them
+template <class KA, class KB>
+static int flow_grid() { return 296; }
+template <class KA, class KB>
+static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t ctl_bytes, stream_t) {
+    using FK = FlowKernel<KA, KB>;
+    using C = cx<typename FK::T>;
+    ++g_launches;
+    std::memset(p.ctl, 0, ctl_bytes);
+    const FlowSched& sc = p.sched;
+    uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
+    uint32_t* freed = ready + (sc.ring_mask + 1);
+    std::vector<typename KA::Regs> ra((size_t)KA::NT);
+    std::vector<typename KB::Regs> rb((size_t)KB::NT);
+    std::vector<C> smem(FK::SMEM_BYTES / sizeof(C) + 1);
+    std::vector<uint32_t> seenA((size_t)sc.batch * sc.TA, 0), seenB((size_t)sc.batch * sc.TB, 0);
+    for (uint32_t ticket = 0; ticket < sc.total; ++ticket) {
+        int kind;
+        uint32_t t, tile;
+        bool valid;
+        sc.decode(ticket, kind, t, tile, valid);
+        if (!valid) continue;
+        const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+        std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
+        if (kind == 0) {
+            if (tile >= sc.TA || freed[slot] < gen * sc.TB) { g_err = "flow: pass-A tile scheduled before its ring slot was free"; return false; }
+            ++seenA[(size_t)t * sc.TA + tile];
+            EmuPhases<KA, 0>::run(p.a, t * sc.TA + tile, ra, smem.data());
+            ++ready[slot];
+        } else {
+            if (tile >= sc.TB || ready[slot] < (gen + 1u) * sc.TA) { g_err = "flow: pass-B tile scheduled before pass A finished"; return false; }
+            ++seenB[(size_t)t * sc.TB + tile];
+            EmuPhases<KB, 0>::run(p.b, t * sc.TB + tile, rb, smem.data());
+            ++freed[slot];
+        }
+    }
+    for (uint32_t v : seenA) if (v != 1) { g_err = "flow: a pass-A tile did not run exactly once"; return false; }
+    for (uint32_t v : seenB) if (v != 1) { g_err = "flow: a pass-B tile did not run exactly once"; return false; }
     return true;
 }
 
