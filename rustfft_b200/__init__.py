@@ -29,7 +29,8 @@ import numpy as np
 __all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "default_library", "shard_range"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB_PATH = os.path.join(_HERE, "libb200fft.so")
+# B200FFT_LIB: load another build of the same C ABI (A/B measurements of kernel variants; tools/ab_two_pass.py)
+DEFAULT_LIB_PATH = os.environ.get("B200FFT_LIB") or os.path.join(_HERE, "libb200fft.so")
 
 F32, F64 = 0, 1
 

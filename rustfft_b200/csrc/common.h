@@ -245,6 +245,21 @@ template <typename T> B2_HD void st_cs(cx<T>* p, cx<T> v) {
     *p = v;
 #endif
 }
+// strong relaxed load at device scope (SASS LDG.E.64.STRONG.GPU): never served from this SM's L1, so data written
+// by other SMs earlier in the SAME launch (the dataflow four-step's ring) is read from L2, the point of coherence
+template <typename T> B2_HD cx<T> ld_strong(const cx<T>* p) {
+#if defined(__CUDA_ARCH__)
+    cx<T> r;
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    } else {
+        asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    }
+    return r;
+#else
+    return *p;
+#endif
+}
 // store into the L2-resident workspace that the next pass re-reads
 template <typename T> B2_HD void st_keep(cx<T>* p, cx<T> v) {
 #if defined(__CUDA_ARCH__)

@@ -23,6 +23,13 @@
 
 namespace b2 {
 
+// largest power of two <= r (constant-folded inside unrolled loops)
+B2_HD constexpr int hibit(int r) {
+    int h = 1;
+    while (2 * h <= r) h *= 2;
+    return h;
+}
+
 enum Map { JF = 0, FF = 1 };  // which index varies fastest across consecutive threads
 
 template <typename T_, int L_, int E_, int F_, typename RL_, int PS_ = 4>
@@ -83,8 +90,27 @@ struct Engine {
             for (int r = 0; r < R; ++r) a[r] = v[u + r * Q];
             if (S > 0) {
                 const cx<T>* t = tw + RL::tw_offset(S) + k;
-                B2_UNROLL
-                for (int r = 1; r < R; ++r) a[r] = cmul(a[r], ldg(t + (r - 1) * p));
+#if defined(B2_TW_FEW)
+                if constexpr (R >= 8 && (R & (R - 1)) == 0 && sizeof(T) == 4) {
+                    // load only W^(k 2^i) and build the other powers as products (each a product of at most
+                    // log2 R correctly rounded table entries): log2 R loads instead of R - 1 through the LSU
+                    cx<T> w[R];
+                    B2_UNROLL
+                    for (int r = 1; r < R; r <<= 1) w[r] = ldg(t + (r - 1) * p);
+                    B2_UNROLL
+                    for (int r = 3; r < R; ++r)
+                        if (r & (r - 1)) {
+                            const int hi = hibit(r);
+                            w[r] = cmul(w[hi], w[r - hi]);
+                        }
+                    B2_UNROLL
+                    for (int r = 1; r < R; ++r) a[r] = cmul(a[r], w[r]);
+                } else
+#endif
+                {
+                    B2_UNROLL
+                    for (int r = 1; r < R; ++r) a[r] = cmul(a[r], ldg(t + (r - 1) * p));
+                }
             }
             Bfly<R, T>::run(a);
             if (last) {

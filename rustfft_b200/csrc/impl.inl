@@ -256,7 +256,9 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
         while (W < forced) W <<= 1;
         return W;
     }
-    while ((uint64_t)(W - 2) * per_round < look && W < 1024) W <<= 1;
+    // pass A runs D = W/2 rounds ahead of pass B and a slot is reused W/2 rounds after pass B read it: both gaps
+    // must exceed the tickets in flight (one per resident CTA, ~300) or tiles stall on their dependencies
+    while ((uint64_t)(W / 2) * per_round < look && W < 1024) W <<= 1;
     // the ring must stay L2 resident: at most 64 MiB, but never fewer than two slots
     while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W >>= 1;
     return W;

@@ -164,9 +164,32 @@ struct LoadRowsTwRing {
     }
     B2_HD cx<T> get(const St& s, int e) const {
         if (!s.ok) return mk<T>(0, 0);
-        // ld.global.cs is a coherent (weak) load: ordered after the acquire of the slot's ready counter
-        return cmul(ld_cs(s.p + e), ldg_stream(s.t + e));
+        // strong (L1-bypassing) load: the slot was written by other SMs during this launch
+        return cmul(ld_strong(s.p + e), ldg_stream(s.t + e));
     }
+#if defined(B2_TWROW_FEW)
+    // all E elements of thread j at once: W_N^(k1 (j + TP q)) = W_N^(k1 j) * W_N^(k1 TP q).  Both factors are entries
+    // of table row k1 (columns j and TP q); only the columns TP 2^i are loaded (the same address for every thread
+    // of a row: a broadcast) and the other powers are built as products -- 1 + log2 E table loads instead of E.
+    static constexpr bool HAS_LOAD_ALL = sizeof(T) == 4;
+    template <int E, int TP>
+    B2_HD void load_all(const St& s, int j, cx<T> (&v)[E]) const {
+        B2_UNROLL
+        for (int q = 0; q < E; ++q) v[q] = ld_strong(s.p + j + TP * q);
+        cx<T> w[E];
+        const cx<T> a = ldg_stream(s.t + j);
+        B2_UNROLL
+        for (int q = 1; q < E; q <<= 1) w[q] = ldg_stream(s.t + TP * q);
+        B2_UNROLL
+        for (int q = 3; q < E; ++q)
+            if (q & (q - 1)) w[q] = cmul(w[hibit(q)], w[q - hibit(q)]);
+        v[0] = cmul(v[0], a);
+        B2_UNROLL
+        for (int q = 1; q < E; ++q) v[q] = cmul(v[q], cmul(a, w[q]));
+    }
+#else
+    static constexpr bool HAS_LOAD_ALL = false;
+#endif
 };
 
 // ------------------------------------------------------------------------------------------
@@ -254,6 +277,10 @@ struct StoreTransposedConv {
 };
 
 // ------------------------------------------------------------------------------------------
+// a Load functor may provide load_all<E, TP>(st, j, v) (all elements of a thread at once) and say so with HAS_LOAD_ALL
+template <class L, class = void> struct load_all_of { static constexpr bool value = false; };
+template <class L> struct load_all_of<L, decltype((void)L::HAS_LOAD_ALL)> { static constexpr bool value = L::HAS_LOAD_ALL; };
+
 template <class G, Map M0, Map M1, class Load, class Store>
 struct FftKernel {
     using T = typename G::T;
@@ -280,8 +307,12 @@ struct FftKernel {
             uint64_t g = (uint64_t)bid * G::F + f;
             if (g >= p.n_fft) g = p.n_fft - 1;
             const auto st = p.load.prep(g, true);
-            B2_UNROLL
-            for (int q = 0; q < G::E; ++q) r.v[q] = p.load.get(st, j + G::TP * q);
+            if constexpr (load_all_of<Load>::value) {
+                p.load.template load_all<G::E, G::TP>(st, j, r.v);
+            } else {
+                B2_UNROLL
+                for (int q = 0; q < G::E; ++q) r.v[q] = p.load.get(st, j + G::TP * q);
+            }
         }
         Eng::template phase<P>(tid, r.v, smem, p.tw);
         if constexpr (P == NPHASE - 1) {
@@ -668,7 +699,7 @@ struct PipeKernel {
 // Work is a single ordered list of tickets handed out by an atomic counter: round r holds the TA tiles of
 // pass A of transform r and the TB tiles of pass B of transform r - D, interleaved, so at any moment the
 // device is reading new input from HBM (A tiles) and writing finished output to HBM (B tiles) while the
-// intermediate lives in a ring of W = D + 2 (power of two) N-element slots that never leaves L2.
+// intermediate lives in a ring of W = 2 D (power of two) N-element slots that never leaves L2.
 //   B(t) may start when all TA tiles of A(t) have been stored     (ready[slot] >= (gen + 1) * TA)
 //   A(t) may start when all TB tiles of B(t - W) have been read   (freed[slot] >= gen * TB)
 // with slot = t mod W, gen = t / W; both counters only grow.  A dependency always points to a SMALLER ticket,
@@ -700,7 +731,7 @@ inline bool make_flow_sched(FlowSched& s, uint64_t batch, uint32_t TA, uint32_t 
     s.TA = TA;
     s.TB = TB;
     s.ring_mask = W - 1;
-    uint32_t D = W > 2 ? W - 2 : 1;
+    uint32_t D = W > 2 ? W / 2 : 1;
     if ((uint64_t)D > batch) D = (uint32_t)batch;
     if (D < 1) D = 1;
     s.D = D;
@@ -767,84 +798,147 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const _
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T_>*>(smem_raw));
 }
 
+// Signals a tile owes to other tiles (thread 0 only):
+//   pend   pass-A tile finished earlier by this CTA whose "ready" count has not been published yet.  Publishing
+//          needs a device-scope fence that waits for the tile's stores to reach L2; it is DEFERRED to the end of
+//          phase 0 of the next tile (by then the stores have long landed, so the fence costs its base latency
+//          only and no warp idles on it), or earlier if this CTA is about to block on a dependency.
+//   freed  pass-B tile: its ring slot may be overwritten once every thread holds its inputs in registers, i.e.
+//          right after the barrier that ends phase 0 (no fence: nothing was written).
+struct FlowHook {
+    uint32_t* pend;
+    uint32_t* freed;
+};
+B2_D void flow_publish(uint32_t*& pend) {
+    if (pend) {
+        __threadfence();
+        atomicAdd(pend, 1u);
+        pend = nullptr;
+    }
+}
 // phases of one tile inside a CTA that may have more threads than the tile's kernel uses
 template <class KT, int NTC, int P>
 struct FlowPhases {
-    static B2_D void run(const typename KT::Params& p, uint32_t bid, int tid, typename KT::Regs& r, cx<typename KT::T>* smem) {
+    static B2_D void run(const typename KT::Params& p, uint32_t bid, int tid, typename KT::Regs& r, cx<typename KT::T>* smem,
+                         FlowHook& hook) {
         if (NTC == KT::NT || tid < KT::NT) KT::template phase<P>(p, bid, tid, r, smem);
+        if constexpr (P == 0) {
+            if (tid == 0) flow_publish(hook.pend);
+        }
         if constexpr (P + 1 < KT::NPHASE) {
             __syncthreads();
-            FlowPhases<KT, NTC, P + 1>::run(p, bid, tid, r, smem);
+            if constexpr (P == 0) {
+                if (tid == 0 && hook.freed) atomicAdd(hook.freed, 1u);
+            }
+            FlowPhases<KT, NTC, P + 1>::run(p, bid, tid, r, smem, hook);
         }
     }
 };
-B2_D uint32_t ld_acquire_u32(const uint32_t* p) {
+B2_D uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// thread 0 spins until *ctr >= target (bounded: a scheduling bug sets the error flag instead of hanging the GPU)
-B2_D void flow_wait(uint32_t* ctl, const uint32_t* ctr, uint32_t target, int tid) {
-    if (tid == 0) {
-        uint32_t spins = 0;
-        while (ld_acquire_u32(ctr) < target) {
-            __nanosleep(spins < 64 ? 32 : 256);
-            if (++spins > (1u << 22) || (spins > 4096 && ld_acquire_u32(ctl + 1) != 0)) {
-                atomicExch(ctl + 1, 1u);
-                break;
-            }
+// spin until *ctr >= target (bounded: a scheduling bug raises the error flag instead of hanging the GPU)
+B2_D void flow_spin(uint32_t* ctl, const uint32_t* ctr, uint32_t target) {
+    uint32_t spins = 0;
+    while (ld_relaxed_u32(ctr) < target) {
+        __nanosleep(spins < 64 ? 32 : 256);
+        if (++spins > (1u << 22) || (spins > 4096 && ld_relaxed_u32(ctl + 1) != 0)) {
+            atomicExch(ctl + 1, 1u);
+            break;
         }
     }
-    __syncthreads();
+}
+struct FlowDep {
+    const uint32_t* ptr;  // nullptr: nothing to wait for
+    uint32_t target;
+};
+B2_D FlowDep flow_dep(const FlowSched& sc, const uint32_t* ready, const uint32_t* freed, uint32_t ticket) {
+    FlowDep d{nullptr, 0u};
+    if (ticket >= sc.total) return d;
+    int kind;
+    uint32_t t, tile;
+    bool valid;
+    sc.decode(ticket, kind, t, tile, valid);
+    if (!valid) return d;
+    const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+    if (kind == 0) {
+        if (gen > 0) {
+            d.ptr = freed + slot;
+            d.target = gen * sc.TB;
+        }
+    } else {
+        d.ptr = ready + slot;
+        d.target = (gen + 1u) * sc.TA;
+    }
+    return d;
 }
 
+// Thread 0 runs a two-deep software pipeline next to the tiles: while tile i is transformed it already holds the
+// ticket of tile i+1, has the ticket of tile i+2 in flight (atomic) and the dependency counter of tile i+1 in
+// flight (relaxed load); both results are first touched at the END of tile i, so neither round trip to L2 sits
+// between two tiles.  A tile is handed to the CTA (shared-memory mailbox) only once its dependency is met.
 template <class KA, class KB>
 __global__ void __launch_bounds__(FlowKernel<KA, KB>::NT, FlowKernel<KA, KB>::MIN_BLOCKS)
 run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
     using FK = FlowKernel<KA, KB>;
     using C = cx<typename FK::T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_ticket[2];
+    __shared__ uint32_t s_next[2];
     C* smem = reinterpret_cast<C*>(smem_raw);
     const int tid = (int)threadIdx.x;
     const FlowSched& sc = p.sched;
     uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
     uint32_t* freed = ready + (sc.ring_mask + 1);
-    if (tid == 0) s_ticket[0] = atomicAdd(p.ctl, 1u);
+    uint32_t tk1 = 0, tk2 = 0;
+    FlowHook hook{nullptr, nullptr};
+    if (tid == 0) {
+        const uint32_t tk0 = atomicAdd(p.ctl, 1u);
+        tk1 = atomicAdd(p.ctl, 1u);
+        const FlowDep d0 = flow_dep(sc, ready, freed, tk0);
+        if (d0.ptr) flow_spin(p.ctl, d0.ptr, d0.target);
+        s_next[0] = tk0;
+    }
     __syncthreads();
     for (uint32_t it = 0;; ++it) {
-        const uint32_t ticket = s_ticket[it & 1u];
+        const uint32_t ticket = s_next[it & 1u];
         if (ticket >= sc.total) break;
-        // next ticket is fetched while this tile runs (its latency never sits between two tiles)
-        if (tid == 0) s_ticket[(it + 1u) & 1u] = atomicAdd(p.ctl, 1u);
+        FlowDep d1{nullptr, 0u};
+        uint32_t dep_val = 0;
+        if (tid == 0) {
+            tk2 = atomicAdd(p.ctl, 1u);
+            d1 = flow_dep(sc, ready, freed, tk1);
+            if (d1.ptr) dep_val = ld_relaxed_u32(d1.ptr);
+        }
         int kind;
         uint32_t t, tile;
         bool valid;
         sc.decode(ticket, kind, t, tile, valid);
         if (valid) {
-            const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+            const uint32_t slot = t & sc.ring_mask;
             if (kind == 0) {
-                if (gen > 0) flow_wait(p.ctl, freed + slot, gen * sc.TB, tid);
                 typename KA::Regs r;
-                FlowPhases<KA, FK::NT, 0>::run(p.a, t * sc.TA + tile, tid, r, smem);
-                __syncthreads();
-                if (tid == 0) {
-                    __threadfence();
-                    atomicAdd(ready + slot, 1u);
-                }
+                hook.freed = nullptr;
+                FlowPhases<KA, FK::NT, 0>::run(p.a, t * sc.TA + tile, tid, r, smem, hook);
+                hook.pend = ready + slot;  // published later (see FlowHook)
             } else {
-                flow_wait(p.ctl, ready + slot, (gen + 1u) * sc.TA, tid);
                 typename KB::Regs r;
-                FlowPhases<KB, FK::NT, 0>::run(p.b, t * sc.TB + tile, tid, r, smem);
-                __syncthreads();
-                if (tid == 0) {
-                    __threadfence();
-                    atomicAdd(freed + slot, 1u);
-                }
+                hook.freed = freed + slot;
+                FlowPhases<KB, FK::NT, 0>::run(p.b, t * sc.TB + tile, tid, r, smem, hook);
             }
         }
-        __syncthreads();  // shared memory and s_ticket are reused by the next tile
+        if (tid == 0) {
+            if (d1.ptr && dep_val < d1.target) {
+                flow_publish(hook.pend);  // never block while other tiles may be waiting for ours
+                flow_spin(p.ctl, d1.ptr, d1.target);
+            }
+            s_next[(it + 1u) & 1u] = tk1;
+            tk1 = tk2;
+        }
+        __syncthreads();  // shared memory is reused by the next tile; mailbox visible
     }
+    if (tid == 0) flow_publish(hook.pend);
 }
 
 template <class KT>
