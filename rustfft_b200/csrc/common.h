@@ -23,6 +23,19 @@
 #define B2_UNROLL
 #endif
 
+// Twiddle loads: by default a radix-R stage loads only W^(k 2^i) (log2 R table entries) and builds the other
+// R-1-log2 R factors as products, and the inter-pass twiddles of a four-step row come from 1 + log2 E table entries
+// per thread instead of E (measured on B200, profiles/r1t: +3..15 % on the one-pass sizes, +2..4 % on the two-pass
+// ones; relative L2 error +5 %, tests/test_emu_parity.py).  -DB2_TW_ALL restores one table load per factor.
+#if !defined(B2_TW_ALL)
+#if !defined(B2_TW_FEW)
+#define B2_TW_FEW 1
+#endif
+#if !defined(B2_TWROW_FEW)
+#define B2_TWROW_FEW 1
+#endif
+#endif
+
 namespace b2 {
 
 // Complex<T> of the reference is repr(C) {re, im} (CHANGELOG.md:139) == float2 / double2.
@@ -274,6 +287,12 @@ template <typename T> B2_HD void st_keep(cx<T>* p, cx<T> v) {
     *p = v;
 #endif
 }
+
+// opaque 128-byte tensor-map descriptor (CUtensorMap of the driver API; built on the host by rt::make_tile_map,
+// consumed by cp.async.bulk.tensor in tma.h).  The CPU replay harness never reads it.
+struct alignas(64) TMap {
+    unsigned long long opaque[16];
+};
 
 // compile-time list of stage radices
 template <int... Rs>

@@ -230,13 +230,14 @@ static int overlap_streams() {
     return v;
 }
 
-// B200FFT_FLOW=0: two-pass plans run as one launch pair per L2 chunk (the round-1 path).  Default: the single-launch
-// dataflow kernel (kernels.h, run_flow).  B200FFT_FLOW_LOOKAHEAD = tickets pass A runs ahead of pass B (default 500),
-// B200FFT_FLOW_W forces the number of ring slots (power of two >= 2).
+// B200FFT_FLOW=1: two-pass plans run as ONE launch of the dataflow kernel (kernels.h, run_flow) instead of one launch pair
+// per L2 chunk.  Opt-in: measured on B200 (profiles/r1t) it reaches 0.30-0.53 of the HBM roofline against 0.42-0.55 for
+// the chunked path -- the per-tile dependency/ticket/fence work costs more than the launch ramps and tails it removes.
+// B200FFT_FLOW_LOOKAHEAD = tickets pass A runs ahead of pass B (default 500), B200FFT_FLOW_W forces the ring slots.
 static bool use_flow() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_FLOW");
-        return !(e && std::atoi(e) == 0);
+        return e && std::atoi(e) == 1;
     }();
     return v;
 }
@@ -262,6 +263,16 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
     // the ring must stay L2 resident: at most 64 MiB, but never fewer than two slots
     while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W >>= 1;
     return W;
+}
+
+// B200FFT_TMA_TILES=1: the chunked two-pass plans move their tiles with TMA tensor copies (kernels.h, TmaTileKernel)
+// whenever the caller's buffers are 16-byte aligned; otherwise, and by default, the LDG/STG passes.
+static bool use_tma_tiles() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_TMA_TILES");
+        return e && std::atoi(e) == 1 && rt::tma_available();
+    }();
+    return v;
 }
 
 // B200FFT_RADIX32=0 disables the radix-32 geometries (A/B measurements)
@@ -355,6 +366,10 @@ struct Builder {
         std::function<bool(const C* work, C* out, uint64_t nb, rt::stream_t)> b;
         uint64_t ctas_per_transform_a = 0, ctas_per_transform_b = 0;  // tiles per transform
         int wave_a = 0, wave_b = 0;                                    // resident CTAs of each kernel
+        // TMA-tiled variants (tensor maps are built per exec call: they hold the caller's pointers)
+        std::function<bool(const TMap& m_in, const TMap& m_ws, const C* in, C* work, uint32_t z_in, uint64_t nb, rt::stream_t)> a_tma;
+        std::function<bool(const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, rt::stream_t)> b_tma;
+        uint32_t f_a = 0, f_b = 0, box_a = 0, box_b = 0;  // tile width and box rows of each pass
     };
     // transforms per L2 chunk: inside [24, 80] MiB of workspace, as close to whole waves as possible for
     // both passes (a 1024-CTA launch on 296 resident CTAs runs 3.46 waves = 13 % idle; 1152 CTAs run 3.89)
@@ -400,6 +415,26 @@ struct Builder {
             p.n_fft = nb << lg2;
             return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
         };
+        if constexpr (G::NS >= 2) {
+            using KM = TmaTileKernel<G, FF, FF, 0, SW>;
+            fns.f_a = G::F;
+            fns.box_a = KM::BOX_ROWS;
+            fns.a_tma = [=](const TMap& m_in, const TMap& m_ws, const C* in, C* work, uint32_t z_in, uint64_t nb, rt::stream_t s) {
+                typename KM::Params p;
+                p.map_in = m_in;
+                p.map_out = m_ws;
+                p.in = in;
+                p.out = work;
+                p.tw = tw;
+                p.full_tw = nullptr;
+                p.n_fft = nb << lg2;
+                p.lgN = lgN;
+                p.lg_other = lg2;
+                p.z_in = z_in;
+                p.z_out = 0;
+                return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
+            };
+        }
         return true;
     }
     template <int L2, bool SW, int V = 0>
@@ -432,6 +467,26 @@ struct Builder {
             p.n_fft = nb << lg1;
             return rt::launch<KT>(p, (p.n_fft + G::F - 1) / G::F, s);
         };
+        if constexpr (G::NS >= 2) {
+            using KM = TmaTileKernel<G, JF, FF, 1, SW>;
+            fns.f_b = G::F;
+            fns.box_b = KM::BOX_ROWS;
+            fns.b_tma = [=](const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, rt::stream_t s) {
+                typename KM::Params p;
+                p.map_in = TMap{};
+                p.map_out = m_out;
+                p.in = work;
+                p.out = out;
+                p.tw = tw;
+                p.full_tw = full_tw;
+                p.n_fft = nb << lg1;
+                p.lgN = lgN;
+                p.lg_other = lg1;
+                p.z_in = 0;
+                p.z_out = z_out;
+                return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
+            };
+        }
         return true;
     }
     template <bool SW>
@@ -587,12 +642,26 @@ struct Builder {
                 }
             }
             bool ok = true;
+            // TMA-tiled passes: tensor maps over the caller's buffers and the workspaces, built per call
+            const bool tma = use_tma_tiles() && fns.a_tma && fns.b_tma && c.batch < (1ull << 31) &&
+                             ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(work)) & 15u) == 0;
+            TMap m_in, m_out, m_ws[4];
+            if (tma) {
+                const bool f64 = sizeof(T) == 8;
+                ok = rt::make_tile_map(&m_in, f64, in, N2, N1, c.batch, fns.f_a, fns.box_a) &&
+                     rt::make_tile_map(&m_out, f64, out, N1, N2, c.batch, fns.f_b, fns.box_b);
+                for (int k = 0; k < ns && ok; ++k)
+                    ok = rt::make_tile_map(&m_ws[k], f64, work + (uint64_t)k * chunk * N, N2, N1, std::min(chunk, c.batch), fns.f_a, fns.box_a);
+            }
             uint64_t idx = 0;
             for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
                 const uint64_t nb = std::min(chunk, c.batch - b0);
                 const int k = (int)(idx % (uint64_t)ns);
                 C* w = work + (uint64_t)k * chunk * N;
-                ok = fns.a(in + b0 * N, w, nb, st[k]) && fns.b(w, out + b0 * N, nb, st[k]);
+                if (tma)
+                    ok = fns.a_tma(m_in, m_ws[k], in, w, (uint32_t)b0, nb, st[k]) && fns.b_tma(m_out, w, out, (uint32_t)b0, nb, st[k]);
+                else
+                    ok = fns.a(in + b0 * N, w, nb, st[k]) && fns.b(w, out + b0 * N, nb, st[k]);
             }
             if (ns > 1) {
                 for (int k = 1; k < ns; ++k) {

@@ -693,6 +693,148 @@ struct PipeKernel {
 };
 
 // ------------------------------------------------------------------------------------------
+// Four-step passes whose tiles move between global and shared memory through TMA (tensor maps).
+//
+// Round-1 ncu of the LDG/STG passes (profiles/r1m_*): top stall = lg_throttle.  A warp request that touches a
+// 64-byte run in each of four 128-byte lines (8-column tiles of 8-byte elements) costs the L1TEX tag stage four
+// passes, and three of the four global accesses of the two passes are of that shape.  Here the LSU issues NO
+// global access for the signal: one thread asks the TMA unit for the whole [L rows x F columns] box (pass A in /
+// out, pass B out; pass B in is one contiguous bulk copy), the tile lands dense in shared memory
+// (element (e, f) at e*F + f, read / written by "f fastest" threads as 256 contiguous bytes per warp: conflict
+// free), and the same buffer is then reused, in place, as the padded exchange buffer of the stages and finally
+// as the dense staging tile of the outgoing TMA store.
+//   phase 0            dense tile -> registers (+ re/im swap of an inverse plan | x inter-pass twiddle)
+//   phase 1 .. NS*2-1  the engine's phases; the last one also writes the dense output tile
+//   last phase         one thread: TMA store of the tile (cp.async.bulk.tensor ... bulk_group) and its drain
+// ROLE 0 = pass A (strided column tile in, same box out to the workspace), ROLE 1 = pass B (F contiguous rows in,
+// transposed box out: out[b][k2][k1]).
+// ------------------------------------------------------------------------------------------
+template <class G, Map M0, Map M1, int ROLE, bool SW>
+struct TmaTileKernel {
+    using T = typename G::T;
+    using Eng = Engine<G, M0, M1>;
+    static constexpr int NT = G::NT;
+    static constexpr int MIN_BLOCKS = default_min_blocks(G::NT, G::E);
+    static constexpr int NPHASE = Eng::NPHASE + 2;
+    static constexpr size_t TILE_ELEMS = (size_t)G::F * G::L;
+    static constexpr size_t BUF_ELEMS = ((TILE_ELEMS > (size_t)G::SMEM_ELEMS ? TILE_ELEMS : (size_t)G::SMEM_ELEMS) + 15) / 16 * 16;
+    static constexpr size_t SMEM_BYTES = BUF_ELEMS * sizeof(cx<T>);
+    static constexpr uint32_t TILE_BYTES = (uint32_t)(TILE_ELEMS * sizeof(cx<T>));
+    static constexpr int BOX_ROWS = G::L < 256 ? G::L : 256;
+    static constexpr int NBOX = G::L / BOX_ROWS;
+    static_assert(G::NS >= 2, "single-stage sizes use the plain kernels");
+    struct Params {
+        TMap map_in;   // ROLE 0: the user's input as [transform][N1 rows][N2 columns]
+        TMap map_out;  // ROLE 0: workspace, same shape;  ROLE 1: the user's output as [transform][N2 rows][N1 columns]
+        const cx<T>* in;       // what map_in describes (ROLE 1: the workspace, source of the bulk copy)
+        cx<T>* out;            // what map_out describes
+        const cx<T>* tw;       // packed stage twiddles
+        const cx<T>* full_tw;  // ROLE 1: inter-pass twiddles [N1][N2]
+        uint64_t n_fft;        // FFTs of this launch (a whole number of tiles)
+        uint32_t lgN, lg_other;  // ROLE 0: lg_other = log2 N2;  ROLE 1: lg_other = log2 N1
+        uint32_t z_in, z_out;    // transform index of this launch's first transform inside `in` / `out`
+    };
+    struct Regs { cx<T> v[G::E]; };
+    struct Where { uint32_t b, c0; };  // transform of the launch, first column (ROLE 0) / first row (ROLE 1) of the tile
+    static B2_HD Where where(const Params& p, uint32_t bid) {
+        const uint64_t g0 = (uint64_t)bid * G::F;
+        return Where{(uint32_t)(g0 >> p.lg_other), (uint32_t)(g0 & ((1ull << p.lg_other) - 1))};
+    }
+
+#if defined(__CUDACC__)
+    static B2_D void issue_load(const Params& p, uint32_t bid, cx<T>* buf, uint64_t* bar) {
+        const Where w = where(p, bid);
+        tma::mbar_arrive_expect_tx(bar, TILE_BYTES);
+        if (ROLE == 0) {
+            B2_UNROLL
+            for (int k = 0; k < NBOX; ++k)
+                tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)(p.z_in + w.b), bar);
+        } else {
+            tma::bulk_g2s(buf, p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
+        }
+    }
+#endif
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs& r, cx<T>* buf) {
+        if constexpr (P == 0) {
+            const Where w = where(p, bid);
+#if !defined(__CUDA_ARCH__)
+            if (tid == 0) {  // CPU replay: the TMA load is a copy
+                if (ROLE == 0) {
+                    const cx<T>* src = p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + w.c0;
+                    for (int e = 0; e < G::L; ++e)
+                        for (int f = 0; f < G::F; ++f) buf[e * G::F + f] = src[((uint64_t)e << p.lg_other) + f];
+                } else {
+                    const cx<T>* src = p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L;
+                    for (size_t i = 0; i < TILE_ELEMS; ++i) buf[i] = src[i];
+                }
+            }
+#endif
+            int f, j;
+            Eng::template owner<0>(tid, f, j);
+            if (ROLE == 0) {
+                const cx<T>* src = buf + (size_t)j * G::F + f;
+                B2_UNROLL
+                for (int q = 0; q < G::E; ++q) {
+                    const cx<T> v = src[(size_t)G::TP * q * G::F];
+                    r.v[q] = SW ? swap_ri(v) : v;
+                }
+            } else {
+                const cx<T>* src = buf + (size_t)f * G::L + j;
+                const cx<T>* t = p.full_tw + (uint64_t)(w.c0 + f) * G::L + j;
+#if defined(B2_TWROW_FEW)
+                if constexpr (sizeof(T) == 4) {
+                    cx<T> wq[G::E];
+                    const cx<T> a = ldg_stream(t);
+                    B2_UNROLL
+                    for (int q = 1; q < G::E; q <<= 1) wq[q] = ldg_stream(t - j + G::TP * q);
+                    B2_UNROLL
+                    for (int q = 3; q < G::E; ++q)
+                        if (q & (q - 1)) wq[q] = cmul(wq[hibit(q)], wq[q - hibit(q)]);
+                    r.v[0] = cmul(src[0], a);
+                    B2_UNROLL
+                    for (int q = 1; q < G::E; ++q) r.v[q] = cmul(src[G::TP * q], cmul(a, wq[q]));
+                } else
+#endif
+                {
+                    B2_UNROLL
+                    for (int q = 0; q < G::E; ++q) r.v[q] = cmul(src[G::TP * q], ldg_stream(t + G::TP * q));
+                }
+            }
+        } else if constexpr (P < NPHASE - 1) {
+            Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
+            if constexpr (P == NPHASE - 2) {
+                // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
+                int f, j;
+                Eng::out_owner(tid, f, j);
+                cx<T>* dst = buf + (size_t)j * G::F + f;
+                B2_UNROLL
+                for (int q = 0; q < G::E; ++q) dst[(size_t)G::TP * q * G::F] = (ROLE == 1 && SW) ? swap_ri(r.v[q]) : r.v[q];
+#if defined(__CUDA_ARCH__)
+                tma::fence_proxy_async();  // generic-proxy writes -> visible to the TMA store below
+#endif
+            }
+        } else {
+            if (tid == 0) {
+                const Where w = where(p, bid);
+#if defined(__CUDA_ARCH__)
+                B2_UNROLL
+                for (int k = 0; k < NBOX; ++k)
+                    tma::tensor_s2g_3d(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)(p.z_out + w.b), buf + (size_t)k * BOX_ROWS * G::F);
+                tma::bulk_commit();
+                tma::bulk_wait_read0();  // shared memory must outlive the store's reads
+#else
+                cx<T>* dst = p.out + ((uint64_t)(p.z_out + w.b) << p.lgN) + w.c0;
+                for (int e = 0; e < G::L; ++e)
+                    for (int f = 0; f < G::F; ++f) dst[((uint64_t)e << p.lg_other) + f] = buf[e * G::F + f];
+#endif
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Single-launch dataflow four-step.
 //
 // One persistent grid (one CTA per resident slot) executes BOTH passes of every transform of a batch.
@@ -939,6 +1081,25 @@ run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
         __syncthreads();  // shared memory is reused by the next tile; mailbox visible
     }
     if (tid == 0) flow_publish(hook.pend);
+}
+
+// TMA-tiled passes: one thread starts the tile's load, everybody waits on the mbarrier it completes on
+template <class KT>
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_tma(const __grid_constant__ typename KT::Params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    using T = typename KT::T;
+    cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+    const int tid = (int)threadIdx.x;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) KT::issue_load(p, blockIdx.x, buf, &bar);
+    tma::mbar_wait(&bar, 0);
+    typename KT::Regs r;
+    PhaseRunner<KT, 0>::run(p, blockIdx.x, tid, r, buf);
 }
 
 template <class KT>

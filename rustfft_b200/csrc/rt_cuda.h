@@ -1,6 +1,7 @@
 // `rt::` runtime layer on the CUDA runtime (streams, events, memory, kernel launches) -- included by every
 // CUDA translation unit of libb200fft.so.  tests/emu/b200fft_emu.cpp provides the same names on the CPU.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -195,6 +196,81 @@ static bool launch_pipelined(const typename KT::Params& p, stream_t s) {
     }
     const unsigned g = (unsigned)((uint64_t)grid < (uint64_t)p.n_items ? grid : (int)p.n_items);
     run_pipelined<KT><<<g, KT::NT, KT::SMEM_BYTES, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
+// ---- TMA tensor maps -----------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).  A map describes
+// `slabs` matrices of `rows` x `inner_cx` complex numbers (row-major, dense) and a box of box_rows x box_cx.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn encode_tiled() {
+    static encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (encode_tiled_fn) nullptr;
+        }
+        return (encode_tiled_fn)p;
+    }();
+    return fn;
+}
+static bool tma_available() { return encode_tiled() != nullptr; }
+static bool make_tile_map(TMap* out, bool f64, const void* base, uint64_t inner_cx, uint64_t rows, uint64_t slabs, uint32_t box_cx,
+                          uint32_t box_rows) {
+    static_assert(sizeof(TMap) == sizeof(CUtensorMap), "TMap must mirror CUtensorMap");
+    encode_tiled_fn fn = encode_tiled();
+    if (!fn) {
+        g_err = "cuTensorMapEncodeTiled is not available";
+        return false;
+    }
+    const uint64_t esz = f64 ? 8 : 4;
+    const cuuint64_t dims[3] = {2 * inner_cx, rows, slabs};
+    const cuuint64_t strides[2] = {2 * inner_cx * esz, 2 * inner_cx * rows * esz};
+    const cuuint32_t box[3] = {2 * box_cx, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+template <class KT>
+static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) {
+    if (ctas == 0) return true;
+    if (ctas > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        if (KT::SMEM_BYTES > 48 * 1024 &&
+            !check(cudaFuncSetAttribute(run_kernel_tma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return false;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, run_kernel_tma<KT>) == cudaSuccess) {
+            const int regs = ((fa.numRegs + 7) / 8) * 8;
+            int want = 65536 / (regs * KT::NT);
+            if (want > 2048 / KT::NT) want = 2048 / KT::NT;
+            if (want < 1) want = 1;
+            const size_t need = (size_t)want * (KT::SMEM_BYTES + 1024);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            cudaFuncSetAttribute(run_kernel_tma<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        cudaGetLastError();
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    run_kernel_tma<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
     return check(cudaGetLastError(), "kernel launch");
 }
 

@@ -49,6 +49,19 @@ B2_D void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// tiled tensor copies through a CUtensorMap (cuTensorMapEncodeTiled on the host): global -> shared completes on
+// `bar`, shared -> global joins the thread's bulk group.  Coordinates are element indices, innermost first.
+B2_D void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+B2_D void tensor_s2g_3d(const void* tmap, int x, int y, int z, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
 B2_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 B2_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 

@@ -99,6 +99,15 @@ static bool launch_pipelined(const typename KT::Params& p, stream_t) {
     return true;
 }
 
+// TMA-tiled passes: the tensor map is never read here -- phase 0 / the last phase of TmaTileKernel copy the box
+static bool tma_available() { return true; }
+static bool make_tile_map(TMap* out, bool, const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t) {
+    std::memset(out, 0, sizeof(*out));
+    return true;
+}
+template <class KT>
+static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) { return launch<KT>(p, ctas, s); }
+
 // single-launch dataflow four-step: ONE emulated CTA takes the tickets in order, so every dependency (which always
 // points to a smaller ticket) must already be satisfied when its tile starts -- checked here; the counters are
 // kept exactly as the device kernel keeps them

@@ -68,7 +68,7 @@ def test_power_of_two_plans(planner, n, desc32, desc64):
 def test_largest_four_step_f32(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     f = check_fft_algorithm(pl, 1 << 20, DIRS[0], np.complex64, control_kind=oracle.PLANNER, chunks=1)
-    assert f.describe() == "FourStep{1024x1024,flow,ring=4}"
+    assert f.describe() == "FourStep{1024x1024}"
 
 
 @pytest.mark.parametrize("n,desc", [
@@ -84,32 +84,29 @@ def test_large_convolution_plans(planner, n, desc):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
-def test_flow_four_step_ring_wraps(lib):
-    """Single-launch dataflow four-step: batch larger than the ring of L2-resident intermediate slots, so every
-    slot is reused (the replay harness also checks that each tile runs exactly once and never before its
-    dependency, tests/emu)."""
+def test_chunked_four_step_matches_unchunked(lib):
+    # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk (the emulation
+    # library is loaded with B200FFT_CHUNK_MB=32, tests/util.py)
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 1 << 16, 70
     x = signal(n * batch, np.complex64, seed=5)
     f = pl.plan_fft_forward(n)
-    assert f.describe() == "FourStep{256x256,flow,ring=32}"
-    assert f.launches(batch) == 1 and f.workspace_bytes(batch) == 512 + 32 * n * 8
+    # B200FFT_CHUNK_MB=32 (fixture) -> 64 transforms of L2 budget, split over the two overlapped streams:
+    # 32 per chunk, two workspaces, ceil(70/32) = 3 chunks x 2 passes
+    assert f.launches(batch) == 6 and f.workspace_bytes(batch) == 2 * 32 * n * 8
     y = x.copy()
     f.process(y)
     for b in (0, 31, 32, 63, 64, 69):
         assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * 16
-    for batch in (1, 2, 3, 33):  # fewer transforms than the look-ahead / than the ring
-        x = signal(n * batch, np.complex64, seed=batch)
-        y = x.copy()
-        f.process(y)
-        assert rel_l2(y, truth(x, n, False)) < 4 * 5.96e-8 * 16
 
 
-@pytest.mark.parametrize("env", [{"B200FFT_FLOW": "0"}, {"B200FFT_FLOW_W": "2"}, {"B200FFT_FLOW_LOOKAHEAD": "3000"}],
-                         ids=["chunked", "ring2", "deep-lookahead"])
+@pytest.mark.parametrize("env", [{"B200FFT_TMA_TILES": "1"}, {"B200FFT_FLOW": "1"}, {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
+                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}],
+                         ids=["tma-tiles", "flow", "flow-ring2", "flow-deep-lookahead"])
 def test_two_pass_variants_in_a_fresh_process(env):
-    """The library reads its switches once per process: the chunked launch-pair path (B200FFT_FLOW=0) and other ring
-    sizes of the dataflow path are replayed in processes of their own."""
+    """The library reads its switches once per process: the TMA-tiled passes (B200FFT_TMA_TILES=1) and the
+    single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the
+    replay harness also checks that every dataflow tile runs exactly once and never before its dependency."""
     import os
     import subprocess
     import sys

@@ -184,14 +184,15 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
 @pytest.mark.parametrize("env", [
     {"B200FFT_PIPELINE": "1"},                      # persistent TMA (cp.async.bulk + mbarrier) kernels
     {"B200FFT_RADIX32": "0"},                       # radix <= 16 geometries
-    {"B200FFT_OVERLAP": "0", "B200FFT_FLOW": "0"},                     # multi-pass chunks on one stream
-    {"B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8", "B200FFT_FLOW": "0"},  # many small chunks over four streams
+    {"B200FFT_OVERLAP": "0"},                     # multi-pass chunks on one stream
+    {"B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8"},  # many small chunks over four streams
     {"B200FFT_HOST_PIPE": "2"},                     # two-stream host-slice path
-    {"B200FFT_FLOW": "0"},                          # two-pass plans as one launch pair per L2 chunk
-    {"B200FFT_FLOW_W": "2"},                        # dataflow two-pass with the smallest ring (every tile waits)
-    {"B200FFT_FLOW_LOOKAHEAD": "3000"},             # ... and with a deep look-ahead
-], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream", "chunked-two-pass",
-        "flow-ring2", "flow-deep"])
+    {"B200FFT_TMA_TILES": "1"},                     # two-pass tiles through TMA tensor copies
+    {"B200FFT_FLOW": "1"},                          # two-pass plans as one launch of the dataflow kernel
+    {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},   # ... with the smallest ring (every tile waits)
+    {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"},  # ... and with a deep look-ahead
+], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream", "tma-tiles",
+        "flow", "flow-ring2", "flow-deep"])
 def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
     import os
     import subprocess
