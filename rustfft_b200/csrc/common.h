@@ -273,6 +273,16 @@ template <typename T> B2_HD cx<T> ld_strong(const cx<T>* p) {
     return *p;
 #endif
 }
+// drop a 128-byte line of dead scratch data from L2 WITHOUT writing it back (PTX discard.global.L2).  Used on the
+// two-pass intermediate right after the second pass has it in registers: measured before this existed
+// (profiles/r1x), 42-92 % of the intermediate was written back to HBM when its dirty lines were evicted.
+B2_HD void l2_discard_line(const void* p128) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p128) : "memory");
+#else
+    (void)p128;
+#endif
+}
 // store into the L2-resident workspace that the next pass re-reads
 template <typename T> B2_HD void st_keep(cx<T>* p, cx<T> v) {
 #if defined(__CUDA_ARCH__)

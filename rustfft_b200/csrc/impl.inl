@@ -248,20 +248,17 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
     }();
     static const uint32_t look = [] {
         const char* e = std::getenv("B200FFT_FLOW_LOOKAHEAD");
-        const int k = e ? std::atoi(e) : 500;
+        const int k = e ? std::atoi(e) : 700;
         return (uint32_t)(k < 1 ? 1 : k);
     }();
-    uint32_t W = 4;
-    if (forced >= 2) {
-        W = 2;
-        while (W < forced) W <<= 1;
-        return W;
-    }
+    if (forced >= 2) return forced;
     // pass A runs D = W/2 rounds ahead of pass B and a slot is reused W/2 rounds after pass B read it: both gaps
-    // must exceed the tickets in flight (one per resident CTA, ~300) or tiles stall on their dependencies
-    while ((uint64_t)(W / 2) * per_round < look && W < 1024) W <<= 1;
+    // must exceed the tickets that are claimed but unfinished (~1.5 per resident CTA, ~450) or tiles stall
+    uint32_t D = (look + per_round - 1) / per_round;
+    if (D < 1) D = 1;
+    uint32_t W = 2 * D;
     // the ring must stay L2 resident: at most 64 MiB, but never fewer than two slots
-    while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W >>= 1;
+    while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W -= 2;
     return W;
 }
 
@@ -271,6 +268,16 @@ static bool use_tma_tiles() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_TMA_TILES");
         return e && std::atoi(e) == 1 && rt::tma_available();
+    }();
+    return v;
+}
+
+// B200FFT_DISCARD=0: keep the consumed intermediate of two-pass plans in L2 until it is evicted (and written back to HBM).
+// Default: the second pass drops the lines it has read with discard.global.L2 -- they are dead scratch data.
+static bool use_discard() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_DISCARD");
+        return !(e && std::atoi(e) == 0);
     }();
     return v;
 }
@@ -432,6 +439,7 @@ struct Builder {
                 p.lg_other = lg2;
                 p.z_in = z_in;
                 p.z_out = 0;
+                p.discard = 0;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -461,7 +469,7 @@ struct Builder {
                 return rt::launch_pipelined<KP>(q, s);
             }
             typename KT::Params p;
-            p.load = LoadRowsTw<T>{work, full_tw, (uint32_t)G::L, lg1};
+            p.load = LoadRowsTw<T>{work, full_tw, (uint32_t)G::L, lg1, use_discard() ? 1u : 0u};
             p.store = StoreTransposed<T, SW>{out, lgN, lg1};
             p.tw = tw;
             p.n_fft = nb << lg1;
@@ -484,6 +492,7 @@ struct Builder {
                 p.lg_other = lg1;
                 p.z_in = 0;
                 p.z_out = z_out;
+                p.discard = use_discard() ? 1u : 0u;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -551,14 +560,19 @@ struct Builder {
                 typename FK::Params p;
                 C* ring = (C*)((char*)work + ctl_bytes);
                 p.a.load = LoadCols<T, SW>{in + b0 * N, lgN, lg2};
-                p.a.store = StoreColsRing<T>{ring, lgN, lg2, W - 1};
+                p.a.store = StoreColsRing<T>{ring, lgN, lg2, W};
                 p.a.tw = twa;
                 p.a.n_fft = nb << lg2;
-                p.b.load = LoadRowsTwRing<T>{ring, full_tw, (uint32_t)L2, lg1, lgN, W - 1};
+                p.b.load = LoadRowsTwRing<T>{ring, full_tw, (uint32_t)L2, lg1, lgN, W, use_discard() ? 1u : 0u};
                 p.b.store = StoreTransposed<T, SW>{out + b0 * N, lgN, lg1};
                 p.b.tw = twb;
                 p.b.n_fft = nb << lg1;
                 p.ctl = (uint32_t*)work;
+                p.trace = nullptr;
+#if defined(B2_FLOW_TRACE)
+                p.trace = (unsigned long long*)((char*)work + ctl_bytes + (uint64_t)W * N * sizeof(C));
+                if (!rt::memset_async(p.trace, 0, (size_t)FLOW_TRACE_CTAS * FLOW_TRACE_WORDS * 8, s)) return false;
+#endif
                 if (!make_flow_sched(p.sched, nb, TA, TB, W)) {
                     rt::g_err = "dataflow schedule overflow";
                     return false;
@@ -601,10 +615,18 @@ struct Builder {
             uint32_t W = 0;
             if (!make_flow_rt(pl, N1, N2, lgN, full_tw, fn, W)) return false;
             const uint64_t Nn = 1ull << lgN;
-            const uint64_t wbytes = flow_ctl_bytes(W) + (uint64_t)W * Nn * sizeof(C);
+            uint64_t wbytes = flow_ctl_bytes(W) + (uint64_t)W * Nn * sizeof(C);
+#if defined(B2_FLOW_TRACE)
+            wbytes += (uint64_t)FLOW_TRACE_CTAS * FLOW_TRACE_WORDS * 8;
+#endif
             pl.work_bytes = [=](uint64_t) { return wbytes; };
             pl.launches = [=](uint64_t batch) { return (batch + (1ull << 24) - 1) >> 24; };
-            pl.exec = [=](const ExecCtx& c) { return fn((const C*)c.in, (C*)c.out, c.work, c.batch, c.stream); };
+            pl.exec = [=](const ExecCtx& c) {
+                rt::set_l2_window(c.work, wbytes);
+                const bool ok = fn((const C*)c.in, (C*)c.out, c.work, c.batch, c.stream);
+                rt::set_l2_window(nullptr, 0);
+                return ok;
+            };
             pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + ",flow,ring=" + std::to_string(W) + "}";
             pl.chunk = W;
             return true;
@@ -653,6 +675,7 @@ struct Builder {
                 for (int k = 0; k < ns && ok; ++k)
                     ok = rt::make_tile_map(&m_ws[k], f64, work + (uint64_t)k * chunk * N, N2, N1, std::min(chunk, c.batch), fns.f_a, fns.box_a);
             }
+            rt::set_l2_window(work, (size_t)ns * std::min(chunk, c.batch) * N * sizeof(C));
             uint64_t idx = 0;
             for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
                 const uint64_t nb = std::min(chunk, c.batch - b0);
@@ -663,6 +686,7 @@ struct Builder {
                 else
                     ok = fns.a(in + b0 * N, w, nb, st[k]) && fns.b(w, out + b0 * N, nb, st[k]);
             }
+            rt::set_l2_window(nullptr, 0);
             if (ns > 1) {
                 for (int k = 1; k < ns; ++k) {
                     rt::event_t ev = rt::event_create();

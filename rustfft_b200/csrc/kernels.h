@@ -107,6 +107,16 @@ struct LoadRowsTw {
     const cx<T>* tw;  // [N1][N2]
     uint32_t len;     // N2
     uint32_t lg1;     // log2 N1
+    uint32_t discard = 0;  // 1: `in` is dead scratch once read -- drop its lines from L2 without write-back
+    // called by every thread once ALL threads of the CTA hold their inputs in registers: the F rows of a tile are
+    // one contiguous, 128-byte aligned block of F*len elements starting at FFT g0
+    B2_HD void tile_done(uint64_t g0, uint32_t n_ffts, int tid, int nt) const {
+        if (!discard) return;
+        const char* base = reinterpret_cast<const char*>(in + g0 * (uint64_t)len);
+        const uint32_t lines = (uint32_t)((uint64_t)n_ffts * len * sizeof(cx<T>) / 128);
+        for (uint32_t l = (uint32_t)tid; l < lines; l += (uint32_t)nt) l2_discard_line(base + (size_t)l * 128);
+    }
+    static constexpr bool HAS_TILE_DONE = true;
     struct St { const cx<T>* p; const cx<T>* t; bool ok; };
     B2_HD St prep(uint64_t g, bool ok) const {
         const uint64_t k1 = g & ((1ull << lg1) - 1);
@@ -135,15 +145,15 @@ struct StoreTransposed {
 };
 
 // ---- ring-addressed workspace functors of the single-launch dataflow four-step (run_flow below) ----
-// The intermediate of transform b lives in slot (b & ring_mask) of a small ring of N-element slots that
+// The intermediate of transform b lives in slot (b mod ring_w) of a small ring of N-element slots that
 // stays L2 resident; everything else is as in StoreCols / LoadRowsTw.
 template <typename T>
 struct StoreColsRing {
     cx<T>* out;
-    uint32_t lgN, lg2, ring_mask;
+    uint32_t lgN, lg2, ring_w;
     struct St { cx<T>* p; bool ok; };
     B2_HD St prep(uint64_t g, bool ok) const {
-        const uint64_t b = (g >> lg2) & ring_mask, c = g & ((1ull << lg2) - 1);
+        const uint64_t b = (uint32_t)(g >> lg2) % ring_w, c = g & ((1ull << lg2) - 1);
         return St{out + (b << lgN) + c, ok};
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
@@ -156,10 +166,19 @@ struct LoadRowsTwRing {
     const cx<T>* tw;  // [N1][N2]
     uint32_t len;     // N2
     uint32_t lg1;     // log2 N1
-    uint32_t lgN, ring_mask;
+    uint32_t lgN, ring_w;
+    uint32_t discard = 0;  // as in LoadRowsTw
+    B2_HD void tile_done(uint64_t g0, uint32_t n_ffts, int tid, int nt) const {
+        if (!discard) return;
+        const uint64_t k1 = g0 & ((1ull << lg1) - 1), b = (uint32_t)(g0 >> lg1) % ring_w;
+        const char* base = reinterpret_cast<const char*>(in + (b << lgN) + k1 * (uint64_t)len);
+        const uint32_t lines = (uint32_t)((uint64_t)n_ffts * len * sizeof(cx<T>) / 128);
+        for (uint32_t l = (uint32_t)tid; l < lines; l += (uint32_t)nt) l2_discard_line(base + (size_t)l * 128);
+    }
+    static constexpr bool HAS_TILE_DONE = true;
     struct St { const cx<T>* p; const cx<T>* t; bool ok; };
     B2_HD St prep(uint64_t g, bool ok) const {
-        const uint64_t k1 = g & ((1ull << lg1) - 1), b = (g >> lg1) & ring_mask;
+        const uint64_t k1 = g & ((1ull << lg1) - 1), b = (uint32_t)(g >> lg1) % ring_w;
         return St{in + (b << lgN) + k1 * (uint64_t)len, tw + k1 * (uint64_t)len, ok};
     }
     B2_HD cx<T> get(const St& s, int e) const {
@@ -281,6 +300,9 @@ struct StoreTransposedConv {
 template <class L, class = void> struct load_all_of { static constexpr bool value = false; };
 template <class L> struct load_all_of<L, decltype((void)L::HAS_LOAD_ALL)> { static constexpr bool value = L::HAS_LOAD_ALL; };
 
+template <class L, class = void> struct tile_done_of { static constexpr bool value = false; };
+template <class L> struct tile_done_of<L, decltype((void)L::HAS_TILE_DONE)> { static constexpr bool value = L::HAS_TILE_DONE; };
+
 template <class G, Map M0, Map M1, class Load, class Store>
 struct FftKernel {
     using T = typename G::T;
@@ -313,6 +335,11 @@ struct FftKernel {
                 B2_UNROLL
                 for (int q = 0; q < G::E; ++q) r.v[q] = p.load.get(st, j + G::TP * q);
             }
+        }
+        if constexpr (P == 1 && tile_done_of<Load>::value) {
+            // the barrier before this phase: every thread of the CTA has consumed its loads
+            const uint64_t g0 = (uint64_t)bid * G::F;
+            if (g0 + G::F <= p.n_fft) p.load.tile_done(g0, (uint32_t)G::F, tid, G::NT);
         }
         Eng::template phase<P>(tid, r.v, smem, p.tw);
         if constexpr (P == NPHASE - 1) {
@@ -733,6 +760,7 @@ struct TmaTileKernel {
         uint64_t n_fft;        // FFTs of this launch (a whole number of tiles)
         uint32_t lgN, lg_other;  // ROLE 0: lg_other = log2 N2;  ROLE 1: lg_other = log2 N1
         uint32_t z_in, z_out;    // transform index of this launch's first transform inside `in` / `out`
+        uint32_t discard;        // ROLE 1: drop the consumed workspace rows from L2 without write-back
     };
     struct Regs { cx<T> v[G::E]; };
     struct Where { uint32_t b, c0; };  // transform of the launch, first column (ROLE 0) / first row (ROLE 1) of the tile
@@ -803,6 +831,13 @@ struct TmaTileKernel {
                 }
             }
         } else if constexpr (P < NPHASE - 1) {
+            if constexpr (P == 1 && ROLE == 1) {
+                if (p.discard) {  // the tile is in shared memory / registers: its workspace rows are dead
+                    const Where w = where(p, bid);
+                    const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L);
+                    for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT) l2_discard_line(base + (size_t)l * 128);
+                }
+            }
             Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
             if constexpr (P == NPHASE - 2) {
                 // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
@@ -841,7 +876,7 @@ struct TmaTileKernel {
 // Work is a single ordered list of tickets handed out by an atomic counter: round r holds the TA tiles of
 // pass A of transform r and the TB tiles of pass B of transform r - D, interleaved, so at any moment the
 // device is reading new input from HBM (A tiles) and writing finished output to HBM (B tiles) while the
-// intermediate lives in a ring of W = 2 D (power of two) N-element slots that never leaves L2.
+// intermediate lives in a ring of W = 2 D N-element slots that never leaves L2.
 //   B(t) may start when all TA tiles of A(t) have been stored     (ready[slot] >= (gen + 1) * TA)
 //   A(t) may start when all TB tiles of B(t - W) have been read   (freed[slot] >= gen * TB)
 // with slot = t mod W, gen = t / W; both counters only grow.  A dependency always points to a SMALLER ticket,
@@ -851,7 +886,7 @@ struct TmaTileKernel {
 // chunk loop, and reads and writes of HBM are mixed at tile granularity instead of per launch.
 // ------------------------------------------------------------------------------------------
 struct FlowSched {
-    uint32_t batch, TA, TB, D, ring_mask, per_round, m, a_big, n_rounds, total;
+    uint32_t batch, TA, TB, D, ring_w, per_round, m, a_big, n_rounds, total;
     B2_HD void decode(uint32_t ticket, int& kind, uint32_t& t, uint32_t& tile, bool& valid) const {
         const uint32_t r = ticket / per_round, i = ticket - r * per_round;
         const uint32_t period = m + 1, k = i / period, j = i - k * period;
@@ -872,7 +907,7 @@ struct FlowSched {
 inline bool make_flow_sched(FlowSched& s, uint64_t batch, uint32_t TA, uint32_t TB, uint32_t W) {
     s.TA = TA;
     s.TB = TB;
-    s.ring_mask = W - 1;
+    s.ring_w = W;
     uint32_t D = W > 2 ? W / 2 : 1;
     if ((uint64_t)D > batch) D = (uint32_t)batch;
     if (D < 1) D = 1;
@@ -903,6 +938,7 @@ struct FlowKernel {
         typename KB::Params b;
         FlowSched sched;
         uint32_t* ctl;
+        unsigned long long* trace;  // (B2_FLOW_TRACE builds) per-CTA time stamps, else unused
     };
 };
 
@@ -940,17 +976,48 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const _
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T_>*>(smem_raw));
 }
 
-// Signals a tile owes to other tiles (thread 0 only):
+// Thread 0's bookkeeping next to the tiles (all of it off the tiles' critical path):
 //   pend   pass-A tile finished earlier by this CTA whose "ready" count has not been published yet.  Publishing
 //          needs a device-scope fence that waits for the tile's stores to reach L2; it is DEFERRED to the end of
 //          phase 0 of the next tile (by then the stores have long landed, so the fence costs its base latency
 //          only and no warp idles on it), or earlier if this CTA is about to block on a dependency.
 //   freed  pass-B tile: its ring slot may be overwritten once every thread holds its inputs in registers, i.e.
 //          right after the barrier that ends phase 0 (no fence: nothing was written).
+//   next   the NEXT ticket is drawn after phase 0 of the current tile and its dependency counter is read after
+//          phase 1, so both round trips to L2 overlap the rest of the tile -- but a CTA never holds more than one
+//          ticket beyond the one it runs for longer than half a tile: tickets claimed and not yet started are tiles
+//          other CTAs may be waiting for (measured with B2_FLOW_TRACE: drawing two tickets ahead made 70 % of the
+//          tiles wait ~4 us on their dependency).
+struct FlowDep {
+    const uint32_t* ptr;  // nullptr: nothing to wait for
+    uint32_t target;
+};
 struct FlowHook {
     uint32_t* pend;
     uint32_t* freed;
+    uint32_t* ctl;
+    const FlowSched* sc;
+    uint32_t next;     // ticket of the next tile
+    FlowDep dep;       // its dependency ...
+    uint32_t dep_val;  // ... and the counter value seen when it was prefetched
+#if defined(B2_FLOW_TRACE)
+    unsigned long long* trace;  // thread 0 of the first CTAs: globaltimer stamps at the phase boundaries of every tile
+    uint32_t n;
+#endif
 };
+#if defined(B2_FLOW_TRACE)
+static constexpr uint32_t FLOW_TRACE_CTAS = 32, FLOW_TRACE_WORDS = 4096;
+B2_D void flow_stamp(FlowHook& h, int tid, unsigned long long tag) {
+    if (tid == 0 && h.trace && h.n + 1 < FLOW_TRACE_WORDS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        h.trace[h.n++] = (t << 8) | tag;
+    }
+}
+#define B2_STAMP(h, tid, tag) flow_stamp(h, tid, tag)
+#else
+#define B2_STAMP(h, tid, tag)
+#endif
 B2_D void flow_publish(uint32_t*& pend) {
     if (pend) {
         __threadfence();
@@ -958,24 +1025,6 @@ B2_D void flow_publish(uint32_t*& pend) {
         pend = nullptr;
     }
 }
-// phases of one tile inside a CTA that may have more threads than the tile's kernel uses
-template <class KT, int NTC, int P>
-struct FlowPhases {
-    static B2_D void run(const typename KT::Params& p, uint32_t bid, int tid, typename KT::Regs& r, cx<typename KT::T>* smem,
-                         FlowHook& hook) {
-        if (NTC == KT::NT || tid < KT::NT) KT::template phase<P>(p, bid, tid, r, smem);
-        if constexpr (P == 0) {
-            if (tid == 0) flow_publish(hook.pend);
-        }
-        if constexpr (P + 1 < KT::NPHASE) {
-            __syncthreads();
-            if constexpr (P == 0) {
-                if (tid == 0 && hook.freed) atomicAdd(hook.freed, 1u);
-            }
-            FlowPhases<KT, NTC, P + 1>::run(p, bid, tid, r, smem, hook);
-        }
-    }
-};
 B2_D uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -992,11 +1041,7 @@ B2_D void flow_spin(uint32_t* ctl, const uint32_t* ctr, uint32_t target) {
         }
     }
 }
-struct FlowDep {
-    const uint32_t* ptr;  // nullptr: nothing to wait for
-    uint32_t target;
-};
-B2_D FlowDep flow_dep(const FlowSched& sc, const uint32_t* ready, const uint32_t* freed, uint32_t ticket) {
+B2_D FlowDep flow_dep(const FlowSched& sc, const uint32_t* ctl, uint32_t ticket) {
     FlowDep d{nullptr, 0u};
     if (ticket >= sc.total) return d;
     int kind;
@@ -1004,7 +1049,9 @@ B2_D FlowDep flow_dep(const FlowSched& sc, const uint32_t* ready, const uint32_t
     bool valid;
     sc.decode(ticket, kind, t, tile, valid);
     if (!valid) return d;
-    const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+    const uint32_t* ready = ctl + FLOW_CTL_HEAD;
+    const uint32_t* freed = ready + sc.ring_w;
+    const uint32_t gen = t / sc.ring_w, slot = t - gen * sc.ring_w;
     if (kind == 0) {
         if (gen > 0) {
             d.ptr = freed + slot;
@@ -1016,11 +1063,39 @@ B2_D FlowDep flow_dep(const FlowSched& sc, const uint32_t* ready, const uint32_t
     }
     return d;
 }
+B2_D void flow_draw_next(FlowHook& h) { h.next = atomicAdd(h.ctl, 1u); }
+B2_D void flow_peek_dep(FlowHook& h) {
+    h.dep = flow_dep(*h.sc, h.ctl, h.next);
+    h.dep_val = h.dep.ptr ? ld_relaxed_u32(h.dep.ptr) : 0u;
+}
+// phases of one tile inside a CTA that may have more threads than the tile's kernel uses
+template <class KT, int NTC, int P>
+struct FlowPhases {
+    static_assert(KT::NPHASE >= 3, "dataflow tiles have at least two stages");
+    static B2_D void run(const typename KT::Params& p, uint32_t bid, int tid, typename KT::Regs& r, cx<typename KT::T>* smem,
+                         FlowHook& hook) {
+        if (NTC == KT::NT || tid < KT::NT) KT::template phase<P>(p, bid, tid, r, smem);
+        B2_STAMP(hook, tid, 0x10 + 2 * P);  // thread 0 finished phase P
+        if constexpr (P == 0) {
+            if (tid == 0) flow_publish(hook.pend);
+        }
+        if constexpr (P + 1 < KT::NPHASE) {
+            __syncthreads();
+            B2_STAMP(hook, tid, 0x11 + 2 * P);  // everybody finished phase P
+            if constexpr (P == 0) {
+                if (tid == 0) {
+                    if (hook.freed) atomicAdd(hook.freed, 1u);
+                    flow_draw_next(hook);
+                }
+            }
+            if constexpr (P == 1) {
+                if (tid == 0) flow_peek_dep(hook);
+            }
+            FlowPhases<KT, NTC, P + 1>::run(p, bid, tid, r, smem, hook);
+        }
+    }
+};
 
-// Thread 0 runs a two-deep software pipeline next to the tiles: while tile i is transformed it already holds the
-// ticket of tile i+1, has the ticket of tile i+2 in flight (atomic) and the dependency counter of tile i+1 in
-// flight (relaxed load); both results are first touched at the END of tile i, so neither round trip to L2 sits
-// between two tiles.  A tile is handed to the CTA (shared-memory mailbox) only once its dependency is met.
 template <class KA, class KB>
 __global__ void __launch_bounds__(FlowKernel<KA, KB>::NT, FlowKernel<KA, KB>::MIN_BLOCKS)
 run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
@@ -1032,33 +1107,36 @@ run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
     const int tid = (int)threadIdx.x;
     const FlowSched& sc = p.sched;
     uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
-    uint32_t* freed = ready + (sc.ring_mask + 1);
-    uint32_t tk1 = 0, tk2 = 0;
-    FlowHook hook{nullptr, nullptr};
+    uint32_t* freed = ready + sc.ring_w;
+    FlowHook hook;
+    hook.pend = nullptr;
+    hook.freed = nullptr;
+    hook.ctl = p.ctl;
+    hook.sc = &sc;
+    hook.next = 0;
+    hook.dep = FlowDep{nullptr, 0u};
+    hook.dep_val = 0;
+#if defined(B2_FLOW_TRACE)
+    hook.trace = (p.trace && blockIdx.x < FLOW_TRACE_CTAS) ? p.trace + (size_t)blockIdx.x * FLOW_TRACE_WORDS : nullptr;
+    hook.n = 0;
+#endif
     if (tid == 0) {
-        const uint32_t tk0 = atomicAdd(p.ctl, 1u);
-        tk1 = atomicAdd(p.ctl, 1u);
-        const FlowDep d0 = flow_dep(sc, ready, freed, tk0);
-        if (d0.ptr) flow_spin(p.ctl, d0.ptr, d0.target);
-        s_next[0] = tk0;
+        flow_draw_next(hook);
+        flow_peek_dep(hook);
+        if (hook.dep.ptr && hook.dep_val < hook.dep.target) flow_spin(p.ctl, hook.dep.ptr, hook.dep.target);
+        s_next[0] = hook.next;
     }
     __syncthreads();
     for (uint32_t it = 0;; ++it) {
         const uint32_t ticket = s_next[it & 1u];
         if (ticket >= sc.total) break;
-        FlowDep d1{nullptr, 0u};
-        uint32_t dep_val = 0;
-        if (tid == 0) {
-            tk2 = atomicAdd(p.ctl, 1u);
-            d1 = flow_dep(sc, ready, freed, tk1);
-            if (d1.ptr) dep_val = ld_relaxed_u32(d1.ptr);
-        }
         int kind;
         uint32_t t, tile;
         bool valid;
         sc.decode(ticket, kind, t, tile, valid);
+        B2_STAMP(hook, tid, valid ? (kind == 0 ? 0x01 : 0x02) : 0x03);  // tile start
         if (valid) {
-            const uint32_t slot = t & sc.ring_mask;
+            const uint32_t slot = t % sc.ring_w;
             if (kind == 0) {
                 typename KA::Regs r;
                 hook.freed = nullptr;
@@ -1069,35 +1147,45 @@ run_flow(const __grid_constant__ typename FlowKernel<KA, KB>::Params p) {
                 hook.freed = freed + slot;
                 FlowPhases<KB, FK::NT, 0>::run(p.b, t * sc.TB + tile, tid, r, smem, hook);
             }
+        } else if (tid == 0) {  // empty ticket (first / last rounds): nothing to overlap with
+            flow_draw_next(hook);
+            flow_peek_dep(hook);
         }
+        B2_STAMP(hook, tid, 0x04);  // tile body done (thread 0)
         if (tid == 0) {
-            if (d1.ptr && dep_val < d1.target) {
+            if (hook.dep.ptr && hook.dep_val < hook.dep.target) {
                 flow_publish(hook.pend);  // never block while other tiles may be waiting for ours
-                flow_spin(p.ctl, d1.ptr, d1.target);
+                flow_spin(p.ctl, hook.dep.ptr, hook.dep.target);
+                B2_STAMP(hook, tid, 0x05);  // had to wait for the next tile's dependency
             }
-            s_next[(it + 1u) & 1u] = tk1;
-            tk1 = tk2;
+            s_next[(it + 1u) & 1u] = hook.next;
         }
         __syncthreads();  // shared memory is reused by the next tile; mailbox visible
     }
     if (tid == 0) flow_publish(hook.pend);
+#if defined(B2_FLOW_TRACE)
+    if (tid == 0 && hook.trace) hook.trace[FLOW_TRACE_WORDS - 1] = hook.n;
+#endif
 }
 
 // TMA-tiled passes: one thread starts the tile's load, everybody waits on the mbarrier it completes on
 template <class KT>
 __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_tma(const __grid_constant__ typename KT::Params p) {
+    // no static shared memory in this kernel: the dynamic window then starts at offset 0 of the CTA's shared memory,
+    // which gives the tile the 128-byte alignment tensor copies need; the mbarrier sits behind the tile
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
     using T = typename KT::T;
-    cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+    unsigned char* base = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);  // (the launch reserves the slack)
+    cx<T>* buf = reinterpret_cast<cx<T>*>(base);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + KT::SMEM_BYTES);
     const int tid = (int)threadIdx.x;
     if (tid == 0) {
-        tma::mbar_init(&bar, 1);
+        tma::mbar_init(bar, 1);
         tma::fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) KT::issue_load(p, blockIdx.x, buf, &bar);
-    tma::mbar_wait(&bar, 0);
+    if (tid == 0) KT::issue_load(p, blockIdx.x, buf, bar);
+    tma::mbar_wait(bar, 0);
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, tid, r, buf);
 }

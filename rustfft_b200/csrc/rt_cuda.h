@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <string>
 
 #include "common.h"
@@ -79,6 +80,73 @@ static void event_destroy(event_t e) { cudaEventDestroy(e); }
 static bool event_record(event_t e, stream_t s) { return check(cudaEventRecord(e, s), "cudaEventRecord"); }
 static bool stream_wait(stream_t s, event_t e) { return check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
 
+// ---- L2 persistence for the L2-resident intermediate of two-pass plans ---------------------------------------
+// B200FFT_L2_PERSIST_MB = N (N > 0): reserve N MiB of L2 for persisting lines (cudaLimitPersistingL2CacheSize, a
+// DEVICE-WIDE setting, hence opt-in) and launch the passes with an access-policy window over their workspace, so the
+// intermediate is protected from eviction by the streamed input/output.  Measured without it (profiles/r1x): 42-92 %
+// of the intermediate is written back to HBM although the second pass still finds it in L2.
+struct L2Window {
+    void* base;
+    size_t bytes;
+};
+static thread_local L2Window g_l2win{nullptr, 0};
+static size_t l2_persist_bytes() {
+    static size_t v = [] {
+        const char* e = std::getenv("B200FFT_L2_PERSIST_MB");
+        const long mb = e ? std::atol(e) : 0;
+        return mb > 0 ? (size_t)mb << 20 : (size_t)0;
+    }();
+    return v;
+}
+// called by a two-pass exec around its launches; returns false (and changes nothing) when persistence is off
+static bool set_l2_window(void* base, size_t bytes) {
+    if (!base || !bytes) {
+        g_l2win = L2Window{nullptr, 0};
+        return false;
+    }
+    if (!l2_persist_bytes()) return false;
+    static std::atomic<uint64_t> configured{0};
+    static std::atomic<size_t> max_window{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return false;
+        const size_t want = std::min<size_t>(l2_persist_bytes(), (size_t)prop.persistingL2CacheMaxSize);
+        if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        max_window.store((size_t)prop.accessPolicyMaxWindowSize, std::memory_order_relaxed);
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    g_l2win = L2Window{base, std::min(bytes, max_window.load(std::memory_order_relaxed))};
+    return true;
+}
+template <class P>
+static bool launch_ex(void (*kern)(P), unsigned grid, unsigned block, size_t smem, stream_t s, const P& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    unsigned na = 0;
+    if (g_l2win.bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = g_l2win.base;
+        attr[0].val.accessPolicyWindow.num_bytes = g_l2win.bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return check(cudaLaunchKernelEx(&cfg, kern, p), "kernel launch");
+}
+
 }  // namespace rt
 }  // namespace b2
 
@@ -142,8 +210,7 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
         return false;
     }
     if (!ensure_configured<KT>()) return false;
-    run_kernel<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
+    return launch_ex(run_kernel<KT>, (unsigned)ctas, KT::NT, KT::SMEM_BYTES, s, p);
 }
 
 // kernels with run-time sized dynamic shared memory (<= max_smem bytes, configured once)
@@ -252,8 +319,8 @@ static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) 
     cudaGetDevice(&dev);
     const uint64_t bit = 1ull << (dev & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
-        if (KT::SMEM_BYTES > 48 * 1024 &&
-            !check(cudaFuncSetAttribute(run_kernel_tma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+        if (KT::SMEM_BYTES + 144 > 48 * 1024 &&
+            !check(cudaFuncSetAttribute(run_kernel_tma<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KT::SMEM_BYTES + 144)),
                    "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
             return false;
         cudaFuncAttributes fa;
@@ -270,8 +337,7 @@ static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) 
         cudaGetLastError();
         configured.fetch_or(bit, std::memory_order_release);
     }
-    run_kernel_tma<KT><<<(unsigned)ctas, KT::NT, KT::SMEM_BYTES, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
+    return launch_ex(run_kernel_tma<KT>, (unsigned)ctas, KT::NT, KT::SMEM_BYTES + 144, s, p);
 }
 
 // single-launch dataflow four-step: persistent grid = resident CTAs (queried once per kernel and device);
@@ -322,8 +388,7 @@ static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t c
     if (grid <= 0) return false;
     if (!memset_async(p.ctl, 0, ctl_bytes, s)) return false;
     const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)grid, (uint64_t)p.sched.total);
-    run_flow<KA, KB><<<g, FK::NT, FK::SMEM_BYTES, s>>>(p);
-    return check(cudaGetLastError(), "kernel launch");
+    return launch_ex(run_flow<KA, KB>, g, FK::NT, FK::SMEM_BYTES, s, p);
 }
 
 }  // namespace rt

@@ -27,6 +27,7 @@ static bool h2d_sync(void* d, const void* h, size_t n) { std::memcpy(d, h, n); r
 static bool h2d_async(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); return true; }
 static bool d2h_async(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); return true; }
 static bool d2d_async(void* dst, const void* src, size_t n, stream_t) { std::memmove(dst, src, n); return true; }
+static bool set_l2_window(void*, size_t) { return false; }
 static bool memset_async(void* d, int v, size_t n, stream_t) { std::memset(d, v, n); return true; }
 static void* malloc_async(size_t n, stream_t) { return std::malloc(n ? n : 1); }
 static void free_async(void* p, stream_t) { std::free(p); }
@@ -121,7 +122,7 @@ static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t c
     std::memset(p.ctl, 0, ctl_bytes);
     const FlowSched& sc = p.sched;
     uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
-    uint32_t* freed = ready + (sc.ring_mask + 1);
+    uint32_t* freed = ready + sc.ring_w;
     std::vector<typename KA::Regs> ra((size_t)KA::NT);
     std::vector<typename KB::Regs> rb((size_t)KB::NT);
     std::vector<C> smem(FK::SMEM_BYTES / sizeof(C) + 1);
@@ -132,7 +133,7 @@ static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t c
         bool valid;
         sc.decode(ticket, kind, t, tile, valid);
         if (!valid) continue;
-        const uint32_t slot = t & sc.ring_mask, gen = t / (sc.ring_mask + 1u);
+        const uint32_t slot = t % sc.ring_w, gen = t / sc.ring_w;
         std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
         if (kind == 0) {
             if (tile >= sc.TA || freed[slot] < gen * sc.TB) { g_err = "flow: pass-A tile scheduled before its ring slot was free"; return false; }

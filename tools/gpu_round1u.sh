@@ -5,9 +5,12 @@ OUT=gpurun_out/r1u
 mkdir -p $OUT
 export PYTHONPATH=$PWD:$PWD/tests
 B200FFT_TMA_TILES=1 timeout 300 python tests/variant_check.py > $OUT/variant_tma.log 2>&1; echo "rc=$?" >> $OUT/variant_tma.log; tail -4 $OUT/variant_tma.log
-timeout 300 python tests/variant_check.py > $OUT/variant_default.log 2>&1; echo "rc=$?" >> $OUT/variant_default.log; tail -2 $OUT/variant_default.log
+if ! grep -q VARIANT-OK $OUT/variant_tma.log; then
+  B200FFT_TMA_TILES=1 timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python tests/tma_small_check.py > $OUT/sanitizer_tma.log 2>&1
+  grep -v "^=========     Host Frame\|^=========         in " $OUT/sanitizer_tma.log | head -60
+  exit 0
+fi
 ALL=10,11,12,13,14,15,16,17,18,19,20
-env timeout 200 python tools/ab_two_pass.py $ALL >> $OUT/ab.log 2>&1
 env B200FFT_TMA_TILES=1 timeout 200 python tools/ab_two_pass.py 15,16,17,18,19,20 >> $OUT/ab.log 2>&1
 env B200FFT_TMA_TILES=1 B200FFT_OVERLAP=0 timeout 200 python tools/ab_two_pass.py 15,16,17,18,19,20 >> $OUT/ab.log 2>&1
 env B200FFT_TMA_TILES=1 B200FFT_STREAMS=3 timeout 200 python tools/ab_two_pass.py 15,16,17,18,19,20 >> $OUT/ab.log 2>&1
