@@ -219,15 +219,17 @@ static bool use_overlap() {
     }();
     return v;
 }
-// number of streams the chunks of a multi-pass plan are spread over (B200FFT_STREAMS, default 2, max 4)
-static int overlap_streams() {
-    static int v = [] {
+// number of streams the chunks of a multi-pass plan are spread over: B200FFT_STREAMS (1..4) or, by default, what
+// measured best on B200 for the plan kind (profiles/r2a): 4 for two-pass plans below 2^20, 3 from 2^20 on, 2 for the
+// four-pass convolution plans
+static int overlap_streams(int auto_default = 2) {
+    static int forced = [] {
         if (!use_overlap()) return 1;
         const char* e = std::getenv("B200FFT_STREAMS");
-        int k = e ? std::atoi(e) : 2;
-        return k < 1 ? 1 : (k > 4 ? 4 : k);
+        const int k = e ? std::atoi(e) : 0;
+        return k < 1 ? 0 : (k > 4 ? 4 : k);
     }();
-    return v;
+    return forced ? forced : auto_default;
 }
 
 // B200FFT_FLOW=1: two-pass plans run as ONE launch of the dataflow kernel (kernels.h, run_flow) instead of one launch pair
@@ -262,12 +264,13 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
     return W;
 }
 
-// B200FFT_TMA_TILES=1: the chunked two-pass plans move their tiles with TMA tensor copies (kernels.h, TmaTileKernel)
-// whenever the caller's buffers are 16-byte aligned; otherwise, and by default, the LDG/STG passes.
+// The chunked two-pass plans move their tiles with TMA tensor copies (kernels.h, TmaTileKernel) whenever the caller's
+// buffers are 16-byte aligned and the driver exports cuTensorMapEncodeTiled; B200FFT_TMA_TILES=0 selects the LDG/STG
+// passes instead (measured on B200, profiles/r2a: TMA tiles +3..11 % at 2^17..2^20).
 static bool use_tma_tiles() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_TMA_TILES");
-        return e && std::atoi(e) == 1 && rt::tma_available();
+        return !(e && std::atoi(e) == 0) && rt::tma_available();
     }();
     return v;
 }
@@ -637,7 +640,7 @@ struct Builder {
         const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
-        const int K = overlap_streams();
+        const int K = overlap_streams(lgN >= 20 ? 3 : 4);
         // K chunks in flight share the L2 budget
         const uint64_t chunk = std::max<uint64_t>(1, pick_chunk(N * sizeof(C), fns) / (uint64_t)K);
         pl.work_bytes = [=](uint64_t batch) {

@@ -736,12 +736,20 @@ struct PipeKernel {
 // ROLE 0 = pass A (strided column tile in, same box out to the workspace), ROLE 1 = pass B (F contiguous rows in,
 // transposed box out: out[b][k2][k1]).
 // ------------------------------------------------------------------------------------------
+template <class G> struct RL_last_pow2 {
+    static constexpr int R = G::RL::get(G::NS - 1);
+    static constexpr bool value = R >= 8 && (R & (R - 1)) == 0;
+};
 template <class G, Map M0, Map M1, int ROLE, bool SW>
 struct TmaTileKernel {
     using T = typename G::T;
     using Eng = Engine<G, M0, M1>;
     static constexpr int NT = G::NT;
+#if defined(B2_TMA_MINB)
+    static constexpr int MIN_BLOCKS = (G::E >= 32 && sizeof(T) == 4) ? B2_TMA_MINB : default_min_blocks(G::NT, G::E);
+#else
     static constexpr int MIN_BLOCKS = default_min_blocks(G::NT, G::E);
+#endif
     static constexpr int NPHASE = Eng::NPHASE + 2;
     static constexpr size_t TILE_ELEMS = (size_t)G::F * G::L;
     static constexpr size_t BUF_ELEMS = ((TILE_ELEMS > (size_t)G::SMEM_ELEMS ? TILE_ELEMS : (size_t)G::SMEM_ELEMS) + 15) / 16 * 16;
@@ -762,8 +770,32 @@ struct TmaTileKernel {
         uint32_t z_in, z_out;    // transform index of this launch's first transform inside `in` / `out`
         uint32_t discard;        // ROLE 1: drop the consumed workspace rows from L2 without write-back
     };
-    struct Regs { cx<T> v[G::E]; };
+    // tables fetched while the tile is in flight (f32, two-stage tiles): the last stage's twiddles and, for pass B,
+    // the row's inter-pass twiddles -- the round-1 capture of these kernels had long_scoreboard (table loads issued
+    // right before their use) as the top stall
+    static constexpr bool PRE = (G::NS == 2) && sizeof(T) == 4 && ((RL_last_pow2<G>::value));
+    static constexpr int LGE = ilog2_c(G::E);
+    struct Regs {
+        cx<T> v[G::E];
+        typename Eng::template TwRegs<G::NS - 1> twl;
+        cx<T> rw[LGE + 1];  // ROLE 1: W^(k1 j), W^(k1 TP 2^i)
+    };
     struct Where { uint32_t b, c0; };  // transform of the launch, first column (ROLE 0) / first row (ROLE 1) of the tile
+    static B2_HD void prefetch(const Params& p, uint32_t bid, int tid, Regs& r) {
+        if constexpr (PRE) {
+            int f, j;
+            Eng::out_owner(tid, f, j);
+            Eng::template load_tw<G::NS - 1>(j, p.tw, r.twl);
+            if (ROLE == 1) {
+                const Where w = where(p, bid);
+                Eng::template owner<0>(tid, f, j);
+                const cx<T>* t = p.full_tw + (uint64_t)(w.c0 + f) * G::L;
+                r.rw[0] = ldg_stream(t + j);
+                B2_UNROLL
+                for (int l = 0; l < LGE; ++l) r.rw[l + 1] = ldg_stream(t + G::TP * (1 << l));
+            }
+        }
+    }
     static B2_HD Where where(const Params& p, uint32_t bid) {
         const uint64_t g0 = (uint64_t)bid * G::F;
         return Where{(uint32_t)(g0 >> p.lg_other), (uint32_t)(g0 & ((1ull << p.lg_other) - 1))};
@@ -788,6 +820,7 @@ struct TmaTileKernel {
         if constexpr (P == 0) {
             const Where w = where(p, bid);
 #if !defined(__CUDA_ARCH__)
+            prefetch(p, bid, tid, r);  // CPU replay (the device does it while the tile is in flight)
             if (tid == 0) {  // CPU replay: the TMA load is a copy
                 if (ROLE == 0) {
                     const cx<T>* src = p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + w.c0;
@@ -814,9 +847,9 @@ struct TmaTileKernel {
 #if defined(B2_TWROW_FEW)
                 if constexpr (sizeof(T) == 4) {
                     cx<T> wq[G::E];
-                    const cx<T> a = ldg_stream(t);
+                    const cx<T> a = PRE ? r.rw[0] : ldg_stream(t);
                     B2_UNROLL
-                    for (int q = 1; q < G::E; q <<= 1) wq[q] = ldg_stream(t - j + G::TP * q);
+                    for (int q = 1, l = 1; q < G::E; q <<= 1, ++l) wq[q] = PRE ? r.rw[l] : ldg_stream(t - j + G::TP * q);
                     B2_UNROLL
                     for (int q = 3; q < G::E; ++q)
                         if (q & (q - 1)) wq[q] = cmul(wq[hibit(q)], wq[q - hibit(q)]);
@@ -838,7 +871,10 @@ struct TmaTileKernel {
                     for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT) l2_discard_line(base + (size_t)l * 128);
                 }
             }
-            Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
+            if constexpr (P == NPHASE - 2 && PRE)
+                Eng::last_phase_pre(tid, r.v, buf, p.tw, r.twl);
+            else
+                Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
             if constexpr (P == NPHASE - 2) {
                 // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
                 int f, j;
@@ -1185,8 +1221,9 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_tma(const _
     }
     __syncthreads();
     if (tid == 0) KT::issue_load(p, blockIdx.x, buf, bar);
-    tma::mbar_wait(bar, 0);
     typename KT::Regs r;
+    KT::prefetch(p, blockIdx.x, tid, r);  // table loads overlap the tile's flight
+    tma::mbar_wait(bar, 0);
     PhaseRunner<KT, 0>::run(p, blockIdx.x, tid, r, buf);
 }
 

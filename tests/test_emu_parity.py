@@ -91,20 +91,20 @@ def test_chunked_four_step_matches_unchunked(lib):
     n, batch = 1 << 16, 70
     x = signal(n * batch, np.complex64, seed=5)
     f = pl.plan_fft_forward(n)
-    # B200FFT_CHUNK_MB=32 (fixture) -> 64 transforms of L2 budget, split over the two overlapped streams:
-    # 32 per chunk, two workspaces, ceil(70/32) = 3 chunks x 2 passes
-    assert f.launches(batch) == 6 and f.workspace_bytes(batch) == 2 * 32 * n * 8
+    # B200FFT_CHUNK_MB=32 (fixture) -> 64 transforms of L2 budget, split over the four overlapped streams:
+    # 16 per chunk, four workspaces, ceil(70/16) = 5 chunks x 2 passes
+    assert f.launches(batch) == 10 and f.workspace_bytes(batch) == 4 * 16 * n * 8
     y = x.copy()
     f.process(y)
     for b in (0, 31, 32, 63, 64, 69):
         assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * 16
 
 
-@pytest.mark.parametrize("env", [{"B200FFT_TMA_TILES": "1"}, {"B200FFT_FLOW": "1"}, {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
+@pytest.mark.parametrize("env", [{"B200FFT_TMA_TILES": "0"}, {"B200FFT_FLOW": "1"}, {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
                                  {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}],
-                         ids=["tma-tiles", "flow", "flow-ring2", "flow-deep-lookahead"])
+                         ids=["ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead"])
 def test_two_pass_variants_in_a_fresh_process(env):
-    """The library reads its switches once per process: the TMA-tiled passes (B200FFT_TMA_TILES=1) and the
+    """The library reads its switches once per process: the LDG/STG passes (B200FFT_TMA_TILES=0; TMA tiles are the default) and the
     single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the
     replay harness also checks that every dataflow tile runs exactly once and never before its dependency."""
     import os

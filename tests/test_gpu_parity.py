@@ -187,11 +187,11 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
     {"B200FFT_OVERLAP": "0"},                     # multi-pass chunks on one stream
     {"B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8"},  # many small chunks over four streams
     {"B200FFT_HOST_PIPE": "2"},                     # two-stream host-slice path
-    {"B200FFT_TMA_TILES": "1"},                     # two-pass tiles through TMA tensor copies
+    {"B200FFT_TMA_TILES": "0"},                     # two-pass tiles through LDG/STG instead of TMA tensor copies
     {"B200FFT_FLOW": "1"},                          # two-pass plans as one launch of the dataflow kernel
     {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},   # ... with the smallest ring (every tile waits)
     {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"},  # ... and with a deep look-ahead
-], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream", "tma-tiles",
+], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream", "ldg-tiles",
         "flow", "flow-ring2", "flow-deep"])
 def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
     import os

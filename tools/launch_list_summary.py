@@ -28,7 +28,13 @@ def main():
         if metric != "gpu__time_duration.sum":
             continue
         name = r[col["Kernel Name"]]
-        if "run_kernel" in name or "run_pipelined" in name:
+        if "TmaTileKernel" in name or "run_flow" in name:
+            m = re.search(r"Geo<(\w+), (\d+), (\d+), (\d+)", name)
+            role = re.search(r">, \d, \d, (\d), \d>", name)
+            kind = "dataflow four-step (both passes)" if "run_flow" in name else (
+                "TMA pass A (cols)" if role and role.group(1) == "0" else "TMA pass B (rows->transposed)")
+            key = f"b2::{'run_flow' if 'run_flow' in name else 'run_kernel_tma'} {kind} {m.group(1)} L={m.group(2)} E={m.group(3)} F={m.group(4)} grid={r[col['Grid Size']]} block={r[col['Block Size']]}"
+        elif "run_kernel" in name or "run_pipelined" in name:
             m = re.search(r"Geo<(\w+), (\d+), (\d+), (\d+)", name)
             kind = ("conv pass A" if "LoadColsConv" in name else "conv pass B" if "StoreTransposedConv" in name else
                     "pass A (cols)" if "LoadCols" in name else "pass B (rows->transposed)" if "StoreTransposed" in name else
