@@ -431,8 +431,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "frac": round(achieved / hbm, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "whole step (every launch in it is one of this repo's FFT passes)",
                          "algorithmic_bytes_per_step": int(step_bytes), "dominant_kernel": dominant,
-                         "traffic_note": "dram__bytes_read+write summed over the launches of one step, ncu --cache-control none "
-                                         "(profiles/traffic.json)" if traffic else None},
+                         "traffic_note": "DRAM bytes of one step from the committed ncu launch list (dram__bytes_read+write, "
+                                         "--cache-control none): mean bytes per CTA of every kernel x the CTAs of a step; "
+                                         "profiles/traffic.json" if traffic else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "other_configs": extras,
         }), flush=True)
     if dist:
