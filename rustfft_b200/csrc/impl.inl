@@ -964,6 +964,113 @@ struct Builder {
         return pl.direction ? make_smooth_t<true>(pl, radices) : make_smooth_t<false>(pl, radices);
     }
 
+    // ---------------- SmoothFourStep: composite N = N1 * N2 above SMOOTH_MAX, every prime factor <= 31 ----------------
+    // (the reference plans such lengths as MixedRadix / GoodThomas trees, src/plan.rs:508-607; here: two passes, the
+    // intermediate in an L2-sized workspace, chunked over the batch like the power-of-two FourStep)
+    static bool smooth_split(uint64_t n, uint32_t& n1, uint32_t& n2) {
+        // N1 <= N2 <= SMOOTH_MAX, N1 as close to sqrt(N) as possible, both factorable into <= 8 stages
+        uint64_t best = 0;
+        for (uint64_t a = 2; a * a <= n; ++a) {
+            if (n % a) continue;
+            const uint64_t b = n / a;
+            if (b > SMOOTH_MAX) continue;
+            std::vector<uint32_t> ra, rb;
+            if (smooth_factor(a, ra) && smooth_factor(b, rb)) best = a;
+        }
+        if (!best) return false;
+        n1 = (uint32_t)best;
+        n2 = (uint32_t)(n / best);
+        return true;
+    }
+    template <class KT>
+    static bool fill_smooth_pass(b200fft_plan& pl, typename KT::Params& base, uint32_t n, const std::vector<uint32_t>& radices) {
+        std::memset(&base, 0, sizeof(base));
+        std::vector<C> tw;
+        uint32_t p = 1;
+        for (size_t s = 0; s < radices.size(); ++s) {
+            const uint32_t R = radices[s];
+            base.radix[s] = R;
+            base.tw_off[s] = (uint32_t)tw.size();
+            base.div_t[s] = make_fastdiv(n / R);
+            base.div_p[s] = make_fastdiv(p);
+            if (s >= 1)
+                for (uint32_t r = 1; r < R; ++r)
+                    for (uint32_t k = 0; k < p; ++k) tw.push_back(hm::twiddle<T>((uint64_t)k * r, (uint64_t)p * R));
+            p *= R;
+        }
+        if (tw.empty()) tw.push_back(mk<T>(1, 0));
+        base.tw = upload(pl, tw);
+        base.n = n;
+        base.n_stages = (uint32_t)radices.size();
+        return base.tw != nullptr;
+    }
+    template <bool SW>
+    static bool make_smooth_four_step_t(b200fft_plan& pl, uint32_t N1, uint32_t N2) {
+        using KA = SmoothPassKernel<T, SW, 1>;
+        using KB = SmoothPassKernel<T, SW, 2>;
+        const uint64_t N = (uint64_t)N1 * N2;
+        std::vector<uint32_t> ra, rb;
+        if (!smooth_factor(N1, ra) || !smooth_factor(N2, rb)) return false;
+        typename KA::Params pa;
+        typename KB::Params pb;
+        if (!fill_smooth_pass<KA>(pl, pa, N1, ra) || !fill_smooth_pass<KB>(pl, pb, N2, rb)) return false;
+        {  // inter-pass twiddles W_N^(k1 n2), [k1][n2], each entry rounded once
+            std::vector<C> t((size_t)N);
+            for (uint64_t k1 = 0; k1 < N1; ++k1)
+                for (uint64_t n2 = 0; n2 < N2; ++n2) t[(size_t)(k1 * N2 + n2)] = hm::twiddle<T>(k1 * n2, N);
+            pb.full_tw = upload(pl, t);
+            if (!pb.full_tw) return false;
+        }
+        pa.NN = pb.NN = N;
+        pa.other = N2;
+        pb.other = N1;
+        pa.div_other = make_fastdiv(N2);
+        pb.div_other = make_fastdiv(N1);
+        // FFTs per CTA: both ping-pong buffers inside 2 * SMOOTH_MAX elements (+ the odd pitch of pass B)
+        const uint32_t FA = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / N1));
+        const uint32_t pitch = N2 | 1u;
+        const uint32_t FB = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / pitch));
+        pa.f_per_cta = FA;
+        pa.pitch = N1;
+        pa.div_f = make_fastdiv(FA);
+        pa.smem_bytes = ra.size() > 1 ? (uint32_t)(2ull * FA * N1 * sizeof(C)) : 0;
+        pb.f_per_cta = FB;
+        pb.pitch = pitch;
+        pb.div_f = make_fastdiv(FB);
+        pb.smem_bytes = rb.size() > 1 ? (uint32_t)(2ull * FB * pitch * sizeof(C)) : 0;
+        const size_t max_smem = 2ull * (SMOOTH_MAX + 64) * sizeof(C);
+        // transforms per chunk: ~32 MiB of intermediate, and FFT indices of a launch must stay below 2^31
+        uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / (N * sizeof(C)));
+        chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(N1, N2));
+        pl.chunk = chunk;
+        pl.work_bytes = [=](uint64_t batch) { return std::min(batch, chunk) * N * sizeof(C); };
+        pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+        pl.exec = [=](const ExecCtx& c) {
+            const C* in = (const C*)c.in;
+            C* out = (C*)c.out;
+            C* work = (C*)c.work;
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                typename KA::Params qa = pa;
+                qa.in = in + b0 * N;
+                qa.out = work;
+                qa.n_fft = nb * N2;
+                if (!rt::launch_dyn<KA>(qa, (qa.n_fft + FA - 1) / FA, qa.smem_bytes, max_smem, c.stream)) return false;
+                typename KB::Params qb = pb;
+                qb.in = work;
+                qb.out = out + b0 * N;
+                qb.n_fft = nb * N1;
+                if (!rt::launch_dyn<KB>(qb, (qb.n_fft + FB - 1) / FB, qb.smem_bytes, max_smem, c.stream)) return false;
+            }
+            return true;
+        };
+        pl.desc = "SmoothFourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        return true;
+    }
+    static bool make_smooth_four_step(b200fft_plan& pl, uint32_t N1, uint32_t N2) {
+        return pl.direction ? make_smooth_four_step_t<true>(pl, N1, N2) : make_smooth_four_step_t<false>(pl, N1, N2);
+    }
+
     // ---------------- Bluestein (fused) ----------------
     static void bluestein_tables(uint64_t n, uint64_t M, std::vector<C>& chirp, std::vector<C>& mult) {
         chirp.resize((size_t)n);
@@ -1113,6 +1220,8 @@ struct Builder {
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^24 are not planned by this build");
         } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
             ok = make_smooth(pl, radices);  // every prime factor <= 31
+        } else if (uint32_t s1 = 0, s2 = 0; n > SMOOTH_MAX && n <= (1ull << 23) && smooth_split(n, s1, s2)) {
+            ok = make_smooth_four_step(pl, s1, s2);  // composite of small primes: two passes instead of Bluestein's four
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {

@@ -638,6 +638,135 @@ struct SmoothKernel {
 };
 
 // ------------------------------------------------------------------------------------------
+// SmoothPassKernel: the two passes of a four-step over a COMPOSITE length N = N1 * N2 whose prime factors are all
+// <= 31 (N1, N2 <= SMOOTH_MAX): the reference's MixedRadix (src/algorithm/mixed_radix.rs:128-158: columns FFT, twiddles,
+// rows FFT, three transposes) with the transposes folded into strided loads / stores, run-time radix lists as in
+// SmoothKernel.  Replaces Bluestein over a power-of-two four-step (four passes over 2-4x the data) for lengths
+// such as 10000, 44100, 48000, 10^6.
+//   MODE 1 (pass A): FFT g = (transform b, column c), g = b*N2 + c; element e at in[b*N + e*N2 + c]; the N1-point
+//                    result k1 goes to work[b*N + k1*N2 + c].  Threads: column fastest (adjacent columns are
+//                    adjacent in memory); shared memory [element][column].
+//   MODE 2 (pass B): FFT g = (b, row k1), g = b*N1 + k1; element e at work[g*N2 + e], times W_N^(k1 e) (table
+//                    [k1][n2], each entry rounded once); the N2-point result k2 goes to out[b*N + k2*N1 + k1].
+//                    Threads: element fastest (contiguous loads) until the last stage, row fastest there
+//                    (adjacent rows are adjacent in the output); shared memory [row][odd pitch].
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SW, int MODE>
+struct SmoothPassKernel {
+    using T_ = T;
+    static constexpr int NT = 256;
+    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int NPHASE = MAX_STAGES;
+    static constexpr size_t SMEM_BYTES = 0;  // run-time sized: Params::smem_bytes
+    struct Params {
+        const cx<T>* in;
+        cx<T>* out;
+        const cx<T>* tw;       // packed stage twiddles of this pass' length (layout as in SmoothKernel)
+        const cx<T>* full_tw;  // MODE 2: W_N^(k1 n2), [N1][N2]
+        uint64_t n_fft;        // FFTs of this launch (< 2^31)
+        uint64_t NN;           // N = N1 * N2
+        uint32_t n;            // length of this pass' FFTs
+        uint32_t other;        // MODE 1: N2 (columns per transform);  MODE 2: N1 (rows per transform)
+        uint32_t n_stages, f_per_cta, pitch, smem_bytes;
+        uint32_t radix[MAX_STAGES];
+        uint32_t tw_off[MAX_STAGES];
+        FastDiv div_t[MAX_STAGES];  // by T_s = n / radix[s]
+        FastDiv div_p[MAX_STAGES];  // by p_s = product of the radices before s
+        FastDiv div_other, div_f;
+    };
+    struct Regs {};
+
+    static B2_HD size_t sidx(const Params& p, uint32_t f, uint32_t e) {
+        return MODE == 1 ? (size_t)e * p.f_per_cta + f : (size_t)f * p.pitch + e;
+    }
+
+    template <int R>
+    static B2_HD void stage(const Params& p, uint32_t bid, int tid, int s, cx<T>* smem) {
+        const uint32_t F = p.f_per_cta;
+        const uint32_t pp = p.div_p[s].d;
+        const uint32_t T_s = p.div_t[s].d;
+        const bool first = (s == 0), last = (s == (int)p.n_stages - 1);
+        const size_t half = (size_t)F * (MODE == 1 ? p.n : p.pitch);
+        const cx<T>* src_buf = smem + (size_t)((s + 1) & 1) * half;
+        cx<T>* dst_buf = smem + (size_t)(s & 1) * half;
+        const cx<T>* tws = p.tw + p.tw_off[s];
+        const bool f_fastest = (MODE == 1) || last;
+        for (uint32_t idx = (uint32_t)tid; idx < F * T_s; idx += NT) {
+            uint32_t f, i;
+            if (f_fastest) {
+                i = p.div_f.div(idx);
+                f = idx - i * F;
+            } else {
+                f = p.div_t[s].div(idx);
+                i = idx - f * T_s;
+            }
+            const uint64_t g = (uint64_t)bid * F + f;
+            if (g >= p.n_fft) continue;
+            const uint32_t b = p.div_other.div((uint32_t)g), c = (uint32_t)g - b * p.other;  // transform, column | row
+            const uint32_t k = i - p.div_p[s].div(i) * pp;
+            cx<T> a[R];
+            if (first) {
+                if (MODE == 1) {
+                    const cx<T>* src = p.in + (uint64_t)b * p.NN + c;
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) {
+                        const cx<T> v = ld_cs(src + (uint64_t)(i + (uint32_t)q * T_s) * p.other);
+                        a[q] = SW ? swap_ri(v) : v;
+                    }
+                } else {
+                    const cx<T>* src = p.in + g * (uint64_t)p.n + i;
+                    const cx<T>* t = p.full_tw + (uint64_t)c * p.n + i;
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) a[q] = cmul(ld_cs(src + (size_t)q * T_s), ldg_stream(t + (size_t)q * T_s));
+                }
+            } else {
+                B2_UNROLL
+                for (int q = 0; q < R; ++q) a[q] = src_buf[sidx(p, f, i + (uint32_t)q * T_s)];
+                B2_UNROLL
+                for (int q = 1; q < R; ++q) a[q] = cmul(a[q], ldg(tws + (size_t)(q - 1) * pp + k));
+            }
+            Bfly<R, T>::run(a);
+            const uint32_t base = (i - k) * R + k;
+            if (last) {
+                cx<T>* dst = p.out + (uint64_t)b * p.NN + c;
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) {
+                    const cx<T> v = (MODE == 2 && SW) ? swap_ri(a[m]) : a[m];
+                    cx<T>* d = dst + (uint64_t)(base + (uint32_t)m * pp) * p.other;
+                    if (MODE == 2) st_cs(d, v); else *d = v;  // pass A's output is re-read from L2 by pass B
+                }
+            } else {
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) dst_buf[sidx(p, f, base + (uint32_t)m * pp)] = a[m];
+            }
+        }
+    }
+
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs&, cx<T>* smem) {
+        if (P >= (int)p.n_stages) return;
+        switch (p.radix[P]) {
+            case 2: stage<2>(p, bid, tid, P, smem); break;
+            case 3: stage<3>(p, bid, tid, P, smem); break;
+            case 4: stage<4>(p, bid, tid, P, smem); break;
+            case 5: stage<5>(p, bid, tid, P, smem); break;
+            case 7: stage<7>(p, bid, tid, P, smem); break;
+            case 8: stage<8>(p, bid, tid, P, smem); break;
+            case 16: stage<16>(p, bid, tid, P, smem); break;
+            case 11: stage<11>(p, bid, tid, P, smem); break;
+            case 13: stage<13>(p, bid, tid, P, smem); break;
+            case 17: stage<17>(p, bid, tid, P, smem); break;
+            case 19: stage<19>(p, bid, tid, P, smem); break;
+            case 23: stage<23>(p, bid, tid, P, smem); break;
+            case 29: stage<29>(p, bid, tid, P, smem); break;
+            case 31: stage<31>(p, bid, tid, P, smem); break;
+            default: break;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Persistent, software-pipelined one-pass kernels (contiguous tiles).
 //
 // A tile = F whole FFTs that are contiguous in global memory (Direct: F transforms; four-step pass B:

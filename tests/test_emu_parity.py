@@ -51,6 +51,37 @@ def test_smooth_plans(planner, n, desc):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=70)  # > F transforms: several CTAs
 
 
+@pytest.mark.parametrize("n,desc", [(5000, "SmoothFourStep{50x100}"), (4225, "SmoothFourStep{65x65}"),
+                                    (10000, "SmoothFourStep{100x100}"), (44100, "SmoothFourStep{210x210}"),
+                                    (29791, "SmoothFourStep{31x961}"), (17017, "SmoothFourStep{119x143}")])
+def test_smooth_four_step_plans(planner, n, desc):
+    """Composite lengths above the one-pass limit whose prime factors are <= 31: two passes over a run-time radix
+    list (the reference: MixedRadix / GoodThomas trees over its butterflies, src/plan.rs:508-607,
+    src/algorithm/mixed_radix.rs:128-158) instead of Bluestein's four."""
+    pl, dtype = planner
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=3)
+    assert f.describe() == desc
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=2)
+
+
+def test_smooth_four_step_chunks_and_large(lib):
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    n, batch = 100000, 45  # 32 MiB of intermediate = 41 transforms per chunk: two chunks, the second ragged
+    f = pl.plan_fft_forward(n)
+    assert f.describe() == "SmoothFourStep{250x400}" and f.launches(batch) == 4
+    x = signal(n * batch, np.complex64, seed=3)
+    y = x.copy()
+    f.process(y)
+    for b in (0, 40, 41, 44):
+        assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * np.log2(n)
+    f = pl.plan_fft_inverse(1000000)
+    assert f.describe() == "SmoothFourStep{1000x1000}"
+    x = signal(1000000, np.complex64, seed=4)
+    y = x.copy()
+    f.process(y)
+    assert rel_l2(y, truth(x, 1000000, True)) < 4 * 5.96e-8 * np.log2(1000000)
+
+
 @pytest.mark.parametrize("n,desc32,desc64", [
     (2048, "Direct{2048}", "Direct{2048}"), (4096, "Direct{4096}", "Direct{4096}"),
     (8192, "Direct{8192}", "Direct{8192}"), (1 << 14, "Direct{16384}", "FourStep{128x128}"),

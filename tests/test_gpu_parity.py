@@ -145,6 +145,17 @@ def test_large_non_power_of_two(planner, n):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
+@pytest.mark.parametrize("n", [4225, 5000, 6000, 10000, 17017, 29791, 44100, 48000, 100000, 196608, 1000000])
+def test_smooth_composites_two_pass(planner, n):
+    """Composite lengths above the one-pass limit, prime factors <= 31: SmoothFourStep (two passes, run-time radix
+    lists) -- the reference plans them as MixedRadix / GoodThomas trees (src/plan.rs:508-607)."""
+    pl, dtype = planner
+    chunks = 60 if n <= 50000 else 3
+    f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=chunks)
+    assert f.describe().startswith("SmoothFourStep{")
+    check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=2)
+
+
 @pytest.mark.parametrize("n", [360, 1000, 1200, 1536, 2000, 2401, 3600, 4000, 143, 961, 1196, 1131, 3683])
 def test_smooth_lengths_native(planner, n):
     """Prime factors <= 31: one-pass run-time-radix kernel (the reference: RadixN / MixedRadix / butterflies
