@@ -404,6 +404,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "gflops": round(5 * 65536 * 16 * 65536 / (ms * 1e-3) / 1e9, 1),
                        "frac_per_gpu": round(16.0 * 65536 * per_rank / (ms * 1e-3) / 1e9 / hbm, 4)})
 
+        # informational: composite lengths of small primes through the two-pass SmoothFourStep plans (not a BASELINE
+        # config; guarded so that a problem here can never cost the bench line)
+        try:
+            for n6, b6 in ((44100, 16384), (1000000, 512)):
+                f6 = planner.plan_fft_forward(n6)
+                ws6 = torch.empty(max(f6.workspace_bytes(b6), 16), dtype=torch.uint8, device=dev)
+
+                def c6():
+                    f6.process_device(src[: b6 * n6], out=dst[: b6 * n6], workspace=ws6)
+
+                ms = timed(c6, 3)
+                extras.append({"config": f"f32 composite N={n6} batch={b6} (informational)", "plan": f6.describe(), "ms": round(ms, 4),
+                               "gflops": round(5 * n6 * math.log2(n6) * b6 / (ms * 1e-3) / 1e9, 1),
+                               "frac": round(16.0 * n6 * b6 / (ms * 1e-3) / 1e9 / hbm, 4)})
+                del ws6
+        except Exception as e:  # pragma: no cover
+            extras.append({"config": "f32 composite lengths (informational)", "error": f"{type(e).__name__}: {e}"[:200]})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle

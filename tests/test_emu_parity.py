@@ -64,6 +64,29 @@ def test_smooth_four_step_plans(planner, n, desc):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=2)
 
 
+def test_random_smooth_composites(planner):
+    """Seeded random products of primes <= 31 between the one-pass limit and 600 000: every radix list / split the
+    planner can produce for SmoothFourStep, against the f64 truth."""
+    import random
+
+    pl, dtype = planner
+    rnd = random.Random(20260923)
+    lo = 4096 if dtype == np.complex64 else 2048
+    for t in range(16):
+        n = 1
+        while n <= lo:
+            n *= rnd.choice([2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31] if rnd.random() < 0.5 else [2, 2, 3, 5])
+        if n > 600000:
+            continue
+        inv = bool(t % 2)
+        f = pl.plan_fft(n, DIRS[1] if inv else DIRS[0])
+        assert f.describe().startswith("SmoothFourStep{"), (n, f.describe())
+        x = signal(2 * n, dtype, seed=n)
+        y = x.copy()
+        f.process(y)
+        assert rel_l2(y, truth(x, n, inv)) <= 4 * (5.96e-8 if dtype == np.complex64 else 1.11e-16) * np.log2(n), (n, f.describe())
+
+
 def test_smooth_four_step_chunks_and_large(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 100000, 45  # 32 MiB of intermediate = 41 transforms per chunk: two chunks, the second ragged
