@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/golden_v1.npz.
+"""Regenerates tests/golden/golden_v1.npz and golden_v2.npz.
 
 The reference (RustFFT) cannot be executed in this environment (no Rust toolchain), so the golden vectors
 are (a) the reference's own known-answer tests, transcribed (src/algorithm/dft.rs:283-398), and (b) outputs
@@ -25,6 +25,9 @@ LENS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12, 13, 16, 17, 24, 27, 31, 32, 59, 64, 9
         1234]
 
 
+LENS2 = [5000, 10000, 32768]  # SmoothFourStep{50x100}, SmoothFourStep{100x100}, FourStep{128x256}
+
+
 def main():
     out = {}
     for name, dtype in (("f32", np.complex64), ("f64", np.complex128)):
@@ -44,6 +47,15 @@ def main():
         out[f"kat_out_{i}"] = np.array(spec, dtype=np.complex64)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz"), **out)
     print("wrote", len(out), "arrays")
+    # second file: lengths of the two-pass plans (TMA-tiled FourStep, SmoothFourStep), added with those plans
+    out2 = {}
+    for name, dtype, lens in (("f32", np.complex64, LENS2), ("f64", np.complex128, LENS2[:1])):
+        for n in lens:
+            x = signal(n, dtype, seed=1000 + n)
+            out2[f"{name}_fwd_{n}"] = oracle.fft(x, n, False)
+            out2[f"{name}_inv_{n}"] = oracle.fft(x, n, True)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v2.npz"), **out2)
+    print("wrote", len(out2), "arrays")
 
 
 if __name__ == "__main__":
