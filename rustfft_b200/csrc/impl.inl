@@ -34,10 +34,12 @@ inline int fail(int code, const std::string& msg) {
 
 // which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
 // harness defines none and gets everything)
-#if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64)
+#if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64)
 #define B2_PART_CABI 1
 #define B2_PART_F32 1
 #define B2_PART_F64 1
+#define B2_PART_SMOOTH32 1
+#define B2_PART_SMOOTH64 1
 #endif
 
 // ---- geometry registry ---------------------------------------------------------------------
@@ -299,9 +301,26 @@ template <> struct HasV1<float, 1024> { static constexpr bool direct = false, ti
 template <> struct HasV1<float, 8192> { static constexpr bool direct = true, tile = false; };
 template <> struct HasV1<float, 16384> { static constexpr bool direct = true, tile = false; };
 
+// The run-time-radix kernels (Smooth, SmoothFourStep: 14 butterfly sizes x 8 stages each) are instantiated in
+// translation units of their own (b200fft_smooth32.cu / b200fft_smooth64.cu) so the library builds in parallel.
+// kind 0: one-pass Smooth plan of pl.len;  kind 1: SmoothFourStep{a x b}
+bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+
 template <typename T>
 struct Builder {
     typedef cx<T> C;
+    static bool smooth_dispatch(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+        if constexpr (sizeof(T) == 4)
+            return build_smooth_f32(pl, kind, a, b);
+        else
+            return build_smooth_f64(pl, kind, a, b);
+    }
+    static bool smooth_build_here(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+        if (kind == 1) return make_smooth_four_step(pl, a, b);
+        std::vector<uint32_t> radices;
+        return smooth_factor(pl.len, radices) && make_smooth(pl, radices);
+    }
 
     // ---------------- Direct ----------------
     template <int L, bool SW, int V = 0>
@@ -1219,9 +1238,9 @@ struct Builder {
             else
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^24 are not planned by this build");
         } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
-            ok = make_smooth(pl, radices);  // every prime factor <= 31
+            ok = smooth_dispatch(pl, 0, 0, 0);  // every prime factor <= 31
         } else if (uint32_t s1 = 0, s2 = 0; n > SMOOTH_MAX && n <= (1ull << 23) && smooth_split(n, s1, s2)) {
-            ok = make_smooth_four_step(pl, s1, s2);  // composite of small primes: two passes instead of Bluestein's four
+            ok = smooth_dispatch(pl, 1, s1, s2);  // composite of small primes: two passes instead of Bluestein's four
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {
@@ -1249,6 +1268,12 @@ int build_plan_f32(b200fft_plan& pl) { return Builder<float>::build(pl); }
 #endif
 #if defined(B2_PART_F64)
 int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
+#endif
+#if defined(B2_PART_SMOOTH32)
+bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here(pl, kind, a, b); }
+#endif
+#if defined(B2_PART_SMOOTH64)
+bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here(pl, kind, a, b); }
 #endif
 
 }  // namespace b2
