@@ -95,14 +95,68 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------
+class NvmlSampler:
+    """SM clock + throttle reasons through NVML every ~5 ms (nvidia-smi -lms 100 yields only 1-3 lines inside a
+    0.2 s timed region).  Entirely optional: any failure leaves `result()` None and the nvidia-smi sampler is used."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def __init__(self, index: int, nvml=None):
+        self.ok, self.samples, self.mask, self.mx, self.stop_flag, self.thread = False, [], 0, None, False, None
+        try:
+            if nvml is None:
+                import pynvml as nvml
+            self.nvml = nvml
+            nvml.nvmlInit()
+            self.h = nvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nvml.nvmlDeviceGetMaxClockInfo(self.h, nvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(get(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if not self.ok:
+            return
+        try:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.ok = False
+
+    def result(self):
+        try:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1)
+            if not self.ok or len(self.samples) < 3:
+                return None
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.mx, "reasons": sorted(n for b, n in self.REASONS if self.mask & b),
+                    "samples": len(sm), "source": "nvml"}
+        except Exception:
+            return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml = NvmlSampler(index)
 
     def start(self):
+        self.nvml.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -117,6 +171,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        fast = self.nvml.result()
+        if fast is not None:
+            if self.proc:
+                try:
+                    self.proc.terminate()
+                    self.proc.wait(timeout=2)
+                except Exception:
+                    pass
+            return fast
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)

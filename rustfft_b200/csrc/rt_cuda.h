@@ -298,9 +298,17 @@ static bool make_tile_map(TMap* out, bool f64, const void* base, uint64_t inner_
     const cuuint64_t strides[2] = {2 * inner_cx * esz, 2 * inner_cx * rows * esz};
     const cuuint32_t box[3] = {2 * box_cx, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    // L2 promotion of the boxes' sectors: none by default (a 64-byte box row must not drag in its 128-byte line's other
+    // half); B200FFT_TMA_L2PROMO=1/2/3 selects 64 / 128 / 256 bytes for A/B measurements
+    static const CUtensorMapL2promotion promo = [] {
+        const char* e = std::getenv("B200FFT_TMA_L2PROMO");
+        const int k = e ? std::atoi(e) : 0;
+        return k == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : k == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+             : k == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    }();
     const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
         return false;
