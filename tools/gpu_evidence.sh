@@ -12,8 +12,10 @@ timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2>> $OUT/bench.err
 # launch list of one whole step (--profile-cold: no warm-up sweep, one timed sweep = every launch of the step),
 # caches left alone between launches so the L2 hand-off between the two passes is the real one
-timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
-   --csv --log-file $OUT/launches.csv python bench.py --profile --profile-cold --steps 1 > $OUT/ncu_list.log 2>&1
+# (a whole step is ~9000 launches = 25 minutes under ncu: r2b spent most of its GPU budget here.  -c bounds it; every
+#  kernel of the step appears within the first 7000 launches and tools/.. scale per-CTA means to the step)
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
+   -c 4000 --csv --log-file $OUT/launches.csv python bench.py --profile --profile-cold --steps 1 --logs 10,11,12,13,14,15,16,18,20 > $OUT/ncu_list.log 2>&1
 python tools/launch_list_summary.py $OUT/launches.csv > $OUT/launch_list_summary.md 2>&1
 gzip -9 $OUT/launches.csv
 # --set full: Direct{4096}, then the two TMA passes of 1024x1024 (third chunk pair)
