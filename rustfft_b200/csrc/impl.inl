@@ -55,6 +55,12 @@ template <typename T, int L, int V = 0> struct TileGeo;    // four-step tiles: F
     template <> struct DirectGeo<T, L, 1> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
 #define B2_TILE_V1(T, L, E, F, ...) \
     template <> struct TileGeo<T, L, 1> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+// 1-in-2^PS padding of the 1024-point radix-32 tile: tests/test_engine_model.py predicts 2-way bank conflicts for the
+// default PS = 4 (ncu agrees: ~10 % of its shared-memory wavefronts are conflict replays) and none for PS = 5.
+// Build-time switch until it has been timed:  make OUT=../libb200fft_ps5.so BUILD=build_ps5 EXTRA=-DB2_TILE1024_PS=5
+#if !defined(B2_TILE1024_PS)
+#define B2_TILE1024_PS 4
+#endif
 
 B2_DIRECT(float, 2, 2, 128, 2)
 B2_DIRECT(float, 4, 4, 128, 4)
@@ -92,7 +98,15 @@ B2_TILE(float, 512, 16, 16, 2, 16, 16)
 B2_TILE(float, 1024, 16, 8, 16, 16, 4)
 // radix-32 variants (f32): every four-step pass becomes two stages = one shared-memory exchange
 B2_TILE_V1(float, 512, 32, 16, 16, 32)
-B2_TILE_V1(float, 1024, 32, 8, 32, 32)
+template <> struct TileGeo<float, 1024, 1> { using type = Geo<float, 1024, 32, 8, Radices<32, 32>, B2_TILE1024_PS>; };
+// "narrow" variants (B200FFT_NARROW=1, experiment queued for the next GPU session): half the columns per tile, 128
+// threads, so an SM holds FOUR independent 32 KiB tiles in different phases instead of two 64 KiB ones at the same
+// register cost; meant to be paired with tensor-map L2 promotion (B200FFT_TMA_L2PROMO=2) so that the first tile to
+// touch a 128-byte line brings in its neighbours' 32-byte runs
+#define B2_TILE_V2(T, L, E, F, ...) \
+    template <> struct TileGeo<T, L, 2> { using type = Geo<T, L, E, F, Radices<__VA_ARGS__>>; };
+B2_TILE_V2(float, 512, 32, 8, 16, 32)
+B2_TILE_V2(float, 1024, 32, 4, 32, 32)
 B2_DIRECT_V1(float, 8192, 32, 1, 16, 16, 32)
 B2_DIRECT_V1(float, 16384, 32, 1, 16, 32, 32)
 
@@ -295,6 +309,16 @@ static bool use_radix32() {
     }();
     return v;
 }
+static bool use_narrow() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_NARROW");
+        return e && std::atoi(e) == 1;
+    }();
+    return v;
+}
+template <typename T, int L> struct HasV2 { static constexpr bool tile = false; };
+template <> struct HasV2<float, 512> { static constexpr bool tile = true; };
+template <> struct HasV2<float, 1024> { static constexpr bool tile = true; };
 template <typename T, int L> struct HasV1 { static constexpr bool direct = false, tile = false; };
 template <> struct HasV1<float, 512> { static constexpr bool direct = false, tile = true; };   // Direct{512,1024}:
 template <> struct HasV1<float, 1024> { static constexpr bool direct = false, tile = true; };  // radix-16 measured faster
@@ -427,6 +451,9 @@ struct Builder {
     }
     template <int L1, bool SW, int V = 0>
     static bool make_pass_a(b200fft_plan& pl, uint32_t lgN, uint32_t lg2, PassFns& fns) {
+        if constexpr (V == 0 && HasV2<T, L1>::tile) {
+            if (use_narrow()) return make_pass_a<L1, SW, 2>(pl, lgN, lg2, fns);
+        }
         if constexpr (V == 0 && HasV1<T, L1>::tile) {
             if (use_radix32()) return make_pass_a<L1, SW, 1>(pl, lgN, lg2, fns);
         }
@@ -469,6 +496,9 @@ struct Builder {
     }
     template <int L2, bool SW, int V = 0>
     static bool make_pass_b(b200fft_plan& pl, uint32_t lgN, uint32_t lg1, const C* full_tw, PassFns& fns) {
+        if constexpr (V == 0 && HasV2<T, L2>::tile) {
+            if (use_narrow()) return make_pass_b<L2, SW, 2>(pl, lgN, lg1, full_tw, fns);
+        }
         if constexpr (V == 0 && HasV1<T, L2>::tile) {
             if (use_radix32()) return make_pass_b<L2, SW, 1>(pl, lgN, lg1, full_tw, fns);
         }

@@ -23,6 +23,16 @@ def main():
             y = x.copy()
             f.process(y)
             assert rel_l2(y, truth(x, n, inv)) <= strict_bound(n, np.complex64), (n, inv, f.describe())
+    if os.environ.get("B200FFT_NARROW") == "1":
+        # the 4- / 8-column tiles only exist for 512- and 1024-point passes: 2^19 = 512 x 1024, 2^20 = 1024 x 1024
+        for n in (1 << 19, 1 << 20):
+            for direction in (rb.FftDirection.Forward, rb.FftDirection.Inverse):
+                inv = direction == rb.FftDirection.Inverse
+                f = pl.plan_fft(n, direction)
+                x = signal(n * 3, np.complex64, seed=n)
+                y = x.copy()
+                f.process(y)
+                assert rel_l2(y, truth(x, n, inv)) <= strict_bound(n, np.complex64), (n, inv, f.describe())
     if flow:
         # fewer transforms than the look-ahead / than the ring, and a batch that wraps the ring twice
         n = 1 << 16

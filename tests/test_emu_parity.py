@@ -155,8 +155,9 @@ def test_chunked_four_step_matches_unchunked(lib):
 
 
 @pytest.mark.parametrize("env", [{"B200FFT_TMA_TILES": "0"}, {"B200FFT_FLOW": "1"}, {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
-                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}],
-                         ids=["ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead"])
+                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}, {"B200FFT_NARROW": "1"},
+                                 {"B200FFT_NARROW": "1", "B200FFT_TMA_TILES": "0"}],
+                         ids=["ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead", "narrow-tma-tiles", "narrow-ldg-tiles"])
 def test_two_pass_variants_in_a_fresh_process(env):
     """The library reads its switches once per process: the LDG/STG passes (B200FFT_TMA_TILES=0; TMA tiles are the default) and the
     single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the

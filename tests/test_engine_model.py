@@ -108,3 +108,14 @@ def _worst_conflict(L, radices, E, F, maps, PS=4, elem_words=2):
 ])
 def test_smem_layout_is_conflict_free_f32(L, radices, E, F, maps):
     assert _worst_conflict(L, radices, E, F, maps) == 1
+
+
+def test_radix32_tiles_bank_model():
+    """The radix-32 geometries: 512 = 16*32 (16 columns) is conflict free with the 1-in-16 pad; 1024 = 32*32 (8 columns) is
+    2-way with it and conflict free with a 1-in-32 pad (impl.inl: B2_TILE1024_PS, queued for a timed A/B)."""
+    assert _worst_conflict(512, [16, 32], 32, 16, ["FF"] * 2) == 1
+    assert _worst_conflict(512, [16, 32], 32, 16, ["JF", "FF"]) == 1
+    assert _worst_conflict(1024, [32, 32], 32, 8, ["FF"] * 2, PS=4) == 2
+    assert _worst_conflict(1024, [32, 32], 32, 8, ["JF", "FF"], PS=4) == 2
+    assert _worst_conflict(1024, [32, 32], 32, 8, ["FF"] * 2, PS=5) == 1
+    assert _worst_conflict(1024, [32, 32], 32, 8, ["JF", "FF"], PS=5) == 1

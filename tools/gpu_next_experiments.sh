@@ -1,6 +1,7 @@
 #!/bin/bash
 # Cheap A/B runs queued for the next GPU session (each line ~10 s on the box; the whole script ~3 GPU-minutes).
 # Results: gpurun_out/next/ab.log -- fractions of the measured HBM roofline per size (tools/ab_two_pass.py).
+# Before `gpurun`, on the CPU side:  (cd rustfft_b200/csrc && make -j5 OUT=../libb200fft_ps5.so BUILD=build_ps5 EXTRA=-DB2_TILE1024_PS=5)
 set -x
 OUT=gpurun_out/next
 mkdir -p $OUT
@@ -11,6 +12,9 @@ for v in "" \
          "B200FFT_TMA_L2PROMO=3" \
          "B200FFT_STREAMS=4 B200FFT_CHUNK_MB=48" \
          "B200FFT_STREAMS=4 B200FFT_CHUNK_MB=80" \
+         "B200FFT_NARROW=1" \
+         "B200FFT_NARROW=1 B200FFT_TMA_L2PROMO=2" \
+         "B200FFT_LIB=$PWD/rustfft_b200/libb200fft_ps5.so" \
          "B200FFT_FLOW=1 B200FFT_FLOW_LOOKAHEAD=1000"; do
   env $v timeout 200 python tools/ab_two_pass.py 14,15,16,17,18,19,20 >> $OUT/ab.log 2>&1
 done
