@@ -15,9 +15,10 @@
 // Build for parity with `-ffp-contract=off` (Rust never fuses mul+add; num-complex's Complex
 // product is the 4-mul/2-add textbook form) -- see oracle/Makefile.
 //
-// Deviation, stated: the hard-coded leaf butterflies 9,11,12,13,17,19,23,24,27,29,31
-// (src/algorithm/butterflies.rs:780-6242, largely generated code) are evaluated here with the
-// naive Dft node; 1,2,3,4,5,6,7,8,16,32 are restated operation-for-operation.
+// Leaf butterflies (src/algorithm/butterflies.rs): 1,2,3,4,5,6,7,8,16,32 and the composite ones 9 (3x3 mixed radix),
+// 12 (4x3 Good-Thomas), 24 (6x4 mixed radix), 27 (9x3 mixed radix) are restated operation for operation; the prime
+// ones 11,13,17,19,23,29,31 -- generated code in the reference (tools/genbutterflies.py, :842-6242) -- are restated
+// as the loop that generator unrolls (same pairing, same summation order, same sign placement).
 
 #include <cmath>
 #include <cstddef>
@@ -474,8 +475,131 @@ template <class T> inline void bf32(Cx<T>* v, bool inv) {  // :6269-6392 (split 
     }
 }
 
+// Butterfly9, :780-841: 3x3 mixed radix (rows r hold inputs r + 3 i)
+template <class T> inline void bf9(Cx<T>* v, bool inv) {
+    const Cx<T> t3 = twiddle<T>(1, 3, inv), w1 = twiddle<T>(1, 9, inv), w2 = twiddle<T>(2, 9, inv), w4 = twiddle<T>(4, 9, inv);
+    Cx<T> s[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 3; ++i) s[r][i] = v[r + 3 * i];
+    for (int r = 0; r < 3; ++r) bf3(s[r], t3);
+    s[1][1] = s[1][1] * w1;
+    s[1][2] = s[1][2] * w2;
+    s[2][1] = s[2][1] * w2;
+    s[2][2] = s[2][2] * w4;
+    for (int c = 0; c < 3; ++c) {
+        Cx<T> col[3] = {s[0][c], s[1][c], s[2][c]};
+        bf3(col, t3);
+        for (int r = 0; r < 3; ++r) v[3 * r + c] = col[r];
+    }
+}
+// Butterfly12, :1091-1166: 4x3 Good-Thomas with hard-coded input / output orders, no twiddles
+template <class T> inline void bf12(Cx<T>* v, bool inv) {
+    static const int in_idx[3][4] = {{0, 3, 6, 9}, {4, 7, 10, 1}, {8, 11, 2, 5}};
+    static const int out_row[12] = {0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2};
+    static const int out_col[12] = {0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3};
+    const Cx<T> t3 = twiddle<T>(1, 3, inv);
+    Cx<T> s[3][4];
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 4; ++i) s[r][i] = v[in_idx[r][i]];
+    for (int r = 0; r < 3; ++r) bf4(s[r], inv);
+    for (int c = 0; c < 4; ++c) {
+        Cx<T> col[3] = {s[0][c], s[1][c], s[2][c]};
+        bf3(col, t3);
+        for (int r = 0; r < 3; ++r) s[r][c] = col[r];
+    }
+    for (int k = 0; k < 12; ++k) v[k] = s[out_row[k]][out_col[k]];
+}
+// Butterfly24, :3427-3587: 6x4 mixed radix (rows r hold inputs r + 4 i), the multiples of 1/8 turn done with rotate_90 / root2
+template <class T> inline void bf24(Cx<T>* v, bool inv) {
+    const Cx<T> t3 = twiddle<T>(1, 3, inv);
+    const Cx<T> w1 = twiddle<T>(1, 24, inv), w2 = twiddle<T>(2, 24, inv), w4 = twiddle<T>(4, 24, inv), w5 = twiddle<T>(5, 24, inv),
+                w8 = twiddle<T>(8, 24, inv), w10 = twiddle<T>(10, 24, inv);
+    const T root2 = (T)std::sqrt(0.5);
+    Cx<T> s[4][6];
+    for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 6; ++i) s[r][i] = v[r + 4 * i];
+    for (int r = 0; r < 4; ++r) bf6(s[r], t3);
+    s[1][1] = s[1][1] * w1;
+    s[1][2] = s[1][2] * w2;
+    s[1][3] = scale(rot90(s[1][3], inv) + s[1][3], root2);
+    s[1][4] = s[1][4] * w4;
+    s[1][5] = s[1][5] * w5;
+    s[2][1] = s[2][1] * w2;
+    s[2][2] = s[2][2] * w4;
+    s[2][3] = rot90(s[2][3], inv);
+    s[2][4] = s[2][4] * w8;
+    s[2][5] = s[2][5] * w10;
+    s[3][1] = scale(rot90(s[3][1], inv) + s[3][1], root2);
+    s[3][2] = rot90(s[3][2], inv);
+    s[3][3] = scale(rot90(s[3][3], inv) - s[3][3], root2);
+    s[3][4] = Cx<T>{-s[3][4].re, -s[3][4].im};
+    s[3][5] = scale(rot90(s[3][5], inv) + s[3][5], -root2);
+    for (int c = 0; c < 6; ++c) {
+        Cx<T> col[4] = {s[0][c], s[1][c], s[2][c], s[3][c]};
+        bf4(col, inv);
+        for (int r = 0; r < 4; ++r) v[6 * r + c] = col[r];
+    }
+}
+// Butterfly27, :3588-3760: 9x3 mixed radix (rows r hold inputs r + 3 i)
+template <class T> inline void bf27(Cx<T>* v, bool inv) {
+    const Cx<T> t3 = twiddle<T>(1, 3, inv);
+    Cx<T> s[3][9];
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < 9; ++i) s[r][i] = v[r + 3 * i];
+    for (int r = 0; r < 3; ++r) bf9(s[r], inv);
+    for (int c = 1; c < 9; ++c) {
+        s[1][c] = s[1][c] * twiddle<T>((usize)c, 27, inv);
+        s[2][c] = s[2][c] * twiddle<T>((usize)(2 * c), 27, inv);
+    }
+    for (int c = 0; c < 9; ++c) {
+        Cx<T> col[3] = {s[0][c], s[1][c], s[2][c]};
+        bf3(col, t3);
+        for (int r = 0; r < 3; ++r) v[9 * r + c] = col[r];
+    }
+}
+// Butterfly11/13/17/19/23/29/31 (:842-6242, generated): with h = (p-1)/2, x_jp = x[j] + x[p-j], x_jn = x[j] - x[p-j],
+//   out[0] = x0 + x_1p + x_2p + ...            (left to right)
+//   a_re = x0.re + sum_j tw(kj).re * x_jp.re,  b_re = sum_j +-tw(kj).im * x_jn.im     (j = 1..h, left to right)
+//   a_im = x0.im + sum_j tw(kj).re * x_jp.im,  b_im = sum_j +-tw(kj).im * x_jn.re
+//   out[k] = (a_re - b_re, a_im + b_im),  out[p-k] = (a_re + b_re, a_im - b_im)
+// where tw(m) for m = kj mod p > h is the stored twiddle(p - m) with its imaginary part negated.
+template <class T> inline void bf_prime(Cx<T>* v, usize p, bool inv) {
+    const usize h = (p - 1) / 2;
+    Cx<T> tw[16], xp[16], xn[16];
+    for (usize j = 1; j <= h; ++j) {
+        tw[j] = twiddle<T>(j, p, inv);
+        xp[j] = v[j] + v[p - j];
+        xn[j] = v[j] - v[p - j];
+    }
+    Cx<T> sum = v[0];
+    for (usize j = 1; j <= h; ++j) sum = sum + xp[j];
+    Cx<T> out[32];
+    out[0] = sum;
+    for (usize k = 1; k <= h; ++k) {
+        T a_re = v[0].re, a_im = v[0].im, b_re = 0, b_im = 0;
+        for (usize j = 1; j <= h; ++j) {
+            usize m = (k * j) % p;
+            const bool neg = m > h;
+            if (neg) m = p - m;
+            const T c = tw[m].re, sn = neg ? -tw[m].im : tw[m].im;
+            a_re = a_re + c * xp[j].re;
+            a_im = a_im + c * xp[j].im;
+            if (j == 1) {
+                b_re = sn * xn[j].im;
+                b_im = sn * xn[j].re;
+            } else {
+                b_re = b_re + sn * xn[j].im;
+                b_im = b_im + sn * xn[j].re;
+            }
+        }
+        out[k] = Cx<T>{a_re - b_re, a_im + b_im};
+        out[p - k] = Cx<T>{a_re + b_re, a_im - b_im};
+    }
+    for (usize k = 0; k < p; ++k) v[k] = out[k];
+}
+
 template <class T>
-struct LeafNode : Node<T> {  // Butterfly1/2/3/4/5/6/7/8/16/32
+struct LeafNode : Node<T> {  // Butterfly1/2/3/4/5/6/7/8/16/32 + 9/12/24/27 + the prime ones 11..31
     Cx<T> t[3];
     LeafNode(usize len, bool inv) : Node<T>(len, inv) {
         if (len == 3 || len == 6) t[0] = twiddle<T>(1, 3, inv);
@@ -487,7 +611,8 @@ struct LeafNode : Node<T> {  // Butterfly1/2/3/4/5/6/7/8/16/32
             for (int i = 0; i < 3; ++i) t[i] = twiddle<T>(i + 1, 7, inv);
     }
     static bool supported(usize n) {
-        return n == 1 || n == 2 || n == 3 || n == 4 || n == 5 || n == 6 || n == 7 || n == 8 || n == 16 || n == 32;
+        return n == 1 || n == 2 || n == 3 || n == 4 || n == 5 || n == 6 || n == 7 || n == 8 || n == 16 || n == 32 || n == 9 ||
+               n == 12 || n == 24 || n == 27 || n == 11 || n == 13 || n == 17 || n == 19 || n == 23 || n == 29 || n == 31;
     }
     void run(Cx<T>* x) override {
         switch (this->len) {
@@ -501,6 +626,11 @@ struct LeafNode : Node<T> {  // Butterfly1/2/3/4/5/6/7/8/16/32
             case 8: bf8(x, this->inv); break;
             case 16: bf16(x, this->inv); break;
             case 32: bf32(x, this->inv); break;
+            case 9: bf9(x, this->inv); break;
+            case 12: bf12(x, this->inv); break;
+            case 24: bf24(x, this->inv); break;
+            case 27: bf27(x, this->inv); break;
+            case 11: case 13: case 17: case 19: case 23: case 29: case 31: bf_prime(x, this->len, this->inv); break;
         }
     }
     std::string describe() const override { return "Butterfly" + std::to_string(this->len); }
