@@ -309,6 +309,14 @@ static bool use_radix32() {
     }();
     return v;
 }
+// B200FFT_PERSIST=1: Direct{16384} runs as a persistent kernel (rt::launch_persistent); queued for a timed A/B
+static bool use_persistent() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_PERSIST");
+        return e && std::atoi(e) == 1;
+    }();
+    return v;
+}
 static bool use_narrow() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_NARROW");
@@ -376,6 +384,9 @@ struct Builder {
             p.store = StoreRows<T, SW>{(C*)c.out, (uint32_t)L};
             p.tw = tw;
             p.n_fft = c.batch;
+            if constexpr (L >= 16384) {  // one CTA per SM: the persistent form is the experiment queued for these
+                if (use_persistent()) return rt::launch_persistent<KT>(p, (c.batch + G::F - 1) / G::F, c.stream);
+            }
             return rt::launch<KT>(p, (c.batch + G::F - 1) / G::F, c.stream);
         };
         pl.launches = [](uint64_t) { return (uint64_t)1; };

@@ -1133,6 +1133,19 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel(const __gri
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));
 }
 
+// persistent form of run_kernel (opt-in, B200FFT_PERSIST=1, one-CTA-per-SM geometries such as Direct{16384}): a resident
+// CTA walks over tiles bid, bid + gridDim.x, ...; the stores of one tile are still draining while the loads of the next
+// are already in flight, and no CTA launch sits between two tiles.  Queued for a timed A/B (not the default).
+template <class KT>
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_persistent(const __grid_constant__ typename KT::Params p, uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (uint32_t bid = blockIdx.x; bid < n_tiles; bid += gridDim.x) {
+        typename KT::Regs r;
+        PhaseRunner<KT, 0>::run(p, bid, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T>*>(smem_raw));
+        __syncthreads();  // shared memory is reused by the next tile
+    }
+}
+
 // same, for kernels whose shared-memory size is run-time data (SmoothKernel)
 template <class KT>
 __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const __grid_constant__ typename KT::Params p) {

@@ -213,6 +213,41 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t s) {
     return launch_ex(run_kernel<KT>, (unsigned)ctas, KT::NT, KT::SMEM_BYTES, s, p);
 }
 
+// persistent variant: grid = resident CTAs of the kernel (queried once per kernel and device)
+template <class KT>
+static bool launch_persistent(const typename KT::Params& p, uint64_t ctas, stream_t s) {
+    if (ctas == 0) return true;
+    if (ctas > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    static std::atomic<int> grid_for_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int grid = grid_for_dev[dev & 63].load(std::memory_order_acquire);
+    if (grid == 0) {
+        if (KT::SMEM_BYTES > 48 * 1024 &&
+            !check(cudaFuncSetAttribute(run_kernel_persistent<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return false;
+        cudaFuncSetAttribute(run_kernel_persistent<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int per_sm = 0, sms = 0;
+        if (!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_kernel_persistent<KT>, KT::NT, KT::SMEM_BYTES),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+            return false;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1 || sms < 1) {
+            g_err = "persistent kernel does not fit on an SM";
+            return false;
+        }
+        grid = per_sm * sms;
+        grid_for_dev[dev & 63].store(grid, std::memory_order_release);
+    }
+    const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)grid, ctas);
+    run_kernel_persistent<KT><<<g, KT::NT, KT::SMEM_BYTES, s>>>(p, (uint32_t)ctas);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
 // kernels with run-time sized dynamic shared memory (<= max_smem bytes, configured once)
 template <class KT>
 static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_bytes, size_t max_smem, stream_t s) {

@@ -72,6 +72,9 @@ static bool launch(const typename KT::Params& p, uint64_t ctas, stream_t) {
 }
 
 template <class KT>
+static bool launch_persistent(const typename KT::Params& p, uint64_t ctas, stream_t s) { return launch<KT>(p, ctas, s); }
+
+template <class KT>
 static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_bytes, size_t, stream_t) {
     ++g_launches;
     std::vector<typename KT::Regs> regs((size_t)KT::NT);
