@@ -309,6 +309,16 @@ static bool use_radix32() {
     }();
     return v;
 }
+// B200FFT_PREFETCH=1: pass B of a chunk issues cp.async.bulk.prefetch.L2 for the input of the same stream's next chunk
+// (DRAM is ~50 % busy in these plans and a pass-A tile spends most of its life waiting for DRAM); queued for a timed A/B,
+// to be tried with a smaller B200FFT_CHUNK_MB since the prefetched input shares L2 with the intermediates
+static bool use_prefetch() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_PREFETCH");
+        return e && std::atoi(e) == 1;
+    }();
+    return v;
+}
 // B200FFT_PERSIST=1: Direct{16384} runs as a persistent kernel (rt::launch_persistent); queued for a timed A/B
 static bool use_persistent() {
     static bool v = [] {
@@ -432,7 +442,7 @@ struct Builder {
         int wave_a = 0, wave_b = 0;                                    // resident CTAs of each kernel
         // TMA-tiled variants (tensor maps are built per exec call: they hold the caller's pointers)
         std::function<bool(const TMap& m_in, const TMap& m_ws, const C* in, C* work, uint32_t z_in, uint64_t nb, rt::stream_t)> a_tma;
-        std::function<bool(const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, rt::stream_t)> b_tma;
+        std::function<bool(const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, const void* pf, uint64_t pf_total, rt::stream_t)> b_tma;
         uint32_t f_a = 0, f_b = 0, box_a = 0, box_b = 0;  // tile width and box rows of each pass
     };
     // transforms per L2 chunk: inside [24, 80] MiB of workspace, as close to whole waves as possible for
@@ -500,6 +510,8 @@ struct Builder {
                 p.z_in = z_in;
                 p.z_out = 0;
                 p.discard = 0;
+                p.pf = nullptr;
+                p.pf_bytes = 0;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -542,7 +554,7 @@ struct Builder {
             using KM = TmaTileKernel<G, JF, FF, 1, SW>;
             fns.f_b = G::F;
             fns.box_b = KM::BOX_ROWS;
-            fns.b_tma = [=](const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, rt::stream_t s) {
+            fns.b_tma = [=](const TMap& m_out, const C* work, C* out, uint32_t z_out, uint64_t nb, const void* pf, uint64_t pf_total, rt::stream_t s) {
                 typename KM::Params p;
                 p.map_in = TMap{};
                 p.map_out = m_out;
@@ -556,7 +568,11 @@ struct Builder {
                 p.z_in = 0;
                 p.z_out = z_out;
                 p.discard = use_discard() ? 1u : 0u;
-                return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
+                const uint64_t ctas = p.n_fft / G::F;
+                const uint64_t share = (pf && ctas) ? std::min<uint64_t>((pf_total / ctas) & ~15ull, 1u << 20) : 0;
+                p.pf = share ? pf : nullptr;
+                p.pf_bytes = (uint32_t)share;
+                return rt::launch_tma<KM>(p, ctas, s);
             };
         }
         return true;
@@ -744,8 +760,14 @@ struct Builder {
                 const uint64_t nb = std::min(chunk, c.batch - b0);
                 const int k = (int)(idx % (uint64_t)ns);
                 C* w = work + (uint64_t)k * chunk * N;
-                if (tma)
-                    ok = fns.a_tma(m_in, m_ws[k], in, w, (uint32_t)b0, nb, st[k]) && fns.b_tma(m_out, w, out, (uint32_t)b0, nb, st[k]);
+                if (tma) {
+                    // opt-in: pass B asks L2 for the input of this stream's NEXT chunk (it starts right after this pass)
+                    const uint64_t nxt = b0 + (uint64_t)ns * chunk;
+                    const void* pf = (use_prefetch() && nxt < c.batch) ? (const void*)(in + nxt * N) : nullptr;
+                    const uint64_t pf_total = pf ? std::min(chunk, c.batch - nxt) * N * sizeof(C) : 0;
+                    ok = fns.a_tma(m_in, m_ws[k], in, w, (uint32_t)b0, nb, st[k]) &&
+                         fns.b_tma(m_out, w, out, (uint32_t)b0, nb, pf, pf_total, st[k]);
+                }
                 else
                     ok = fns.a(in + b0 * N, w, nb, st[k]) && fns.b(w, out + b0 * N, nb, st[k]);
             }

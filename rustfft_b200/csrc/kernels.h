@@ -898,6 +898,8 @@ struct TmaTileKernel {
         uint32_t lgN, lg_other;  // ROLE 0: lg_other = log2 N2;  ROLE 1: lg_other = log2 N1
         uint32_t z_in, z_out;    // transform index of this launch's first transform inside `in` / `out`
         uint32_t discard;        // ROLE 1: drop the consumed workspace rows from L2 without write-back
+        const void* pf;          // ROLE 1, opt-in (B200FFT_PREFETCH=1): input of the NEXT chunk of this stream; every CTA asks
+        uint32_t pf_bytes;       //   L2 to fetch its pf_bytes share of it while this pass is still writing output
     };
     // tables fetched while the tile is in flight (f32, two-stage tiles): the last stage's twiddles and, for pass B,
     // the row's inter-pass twiddles -- the round-1 capture of these kernels had long_scoreboard (table loads issued
@@ -940,6 +942,7 @@ struct TmaTileKernel {
                 tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)(p.z_in + w.b), bar);
         } else {
             tma::bulk_g2s(buf, p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
+            if (p.pf != nullptr && p.pf_bytes) tma::bulk_prefetch_l2(static_cast<const char*>(p.pf) + (uint64_t)bid * p.pf_bytes, p.pf_bytes);
         }
     }
 #endif

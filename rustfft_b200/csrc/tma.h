@@ -62,6 +62,10 @@ B2_D void tensor_s2g_3d(const void* tmap, int x, int y, int z, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)
                  : "memory");
 }
+// ask L2 to fetch a contiguous global range (no destination: a pure prefetch, SASS UBLKPF); bytes a multiple of 16
+B2_D void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 B2_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 B2_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 

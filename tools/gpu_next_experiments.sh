@@ -13,6 +13,8 @@ for v in "" \
          "B200FFT_STREAMS=4 B200FFT_CHUNK_MB=48" \
          "B200FFT_STREAMS=4 B200FFT_CHUNK_MB=80" \
          "B200FFT_PERSIST=1" \
+         "B200FFT_PREFETCH=1" \
+         "B200FFT_PREFETCH=1 B200FFT_CHUNK_MB=32" \
          "B200FFT_NARROW=1" \
          "B200FFT_NARROW=1 B200FFT_TMA_L2PROMO=2" \
          "B200FFT_LIB=$PWD/rustfft_b200/libb200fft_ps5.so" \
