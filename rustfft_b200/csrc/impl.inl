@@ -21,7 +21,7 @@
 
 #include "../../include/b200fft.h"
 #include "host_math.h"
-#include "kernels.h"
+#include "fused.h"
 
 namespace b2 {
 
@@ -34,7 +34,9 @@ inline int fail(int code, const std::string& msg) {
 
 // which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
 // harness defines none and gets everything)
-#if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64)
+#if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64) && \
+    !defined(B2_PART_FUSED32)
+#define B2_PART_FUSED32 1
 #define B2_PART_CABI 1
 #define B2_PART_F32 1
 #define B2_PART_F64 1
@@ -121,6 +123,19 @@ B2_TILE(float, 2048, 32, 4, 2, 32, 32)
 B2_TILE(float, 4096, 32, 2, 4, 32, 32)
 B2_TILE(double, 2048, 8, 2, 4, 8, 8, 8)
 B2_TILE(double, 4096, 8, 1, 8, 8, 8, 8)
+
+// tiles of the fused single-launch four-step (fused.h): 32 elements per thread, 256 threads per consumer group, every
+// tile 8192 elements = 64 KiB whatever the pass length -- (columns | rows) per tile = 8192 / L
+template <typename T, int L> struct FusedGeo;
+#define B2_FUSED(L, F, ...) \
+    template <> struct FusedGeo<float, L> { using type = Geo<float, L, 32, F, Radices<__VA_ARGS__>>; };
+B2_FUSED(128, 64, 4, 32)
+B2_FUSED(256, 32, 8, 32)
+B2_FUSED(512, 16, 16, 32)
+template <> struct FusedGeo<float, 1024> { using type = Geo<float, 1024, 32, 8, Radices<32, 32>, B2_TILE1024_PS>; };
+B2_FUSED(2048, 4, 2, 32, 32)
+B2_FUSED(4096, 2, 4, 32, 32)
+static constexpr int FUSED_NG = 2, FUSED_NS = 3;  // consumer groups, shared-memory stages
 
 // largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
 template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
@@ -280,6 +295,42 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
     return W;
 }
 
+// Power-of-two two-pass plans (f32) run as ONE launch of the fused warp-specialised kernel (fused.h) whenever the
+// buffers allow TMA; B200FFT_FUSED=0 selects the chunked launch pairs instead.  B200FFT_FUSED_LOOKAHEAD = tickets pass A
+// runs ahead of pass B (default 600 ~ the tiles in flight on 148 SMs), B200FFT_FUSED_W forces the ring slots,
+// B200FFT_FUSED_NOCOMPUTE=1 skips the butterflies (memory-pipeline ceiling; results are garbage).
+static bool use_fused() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_FUSED");
+        return !(e && std::atoi(e) == 0) && rt::tma_available();
+    }();
+    return v;
+}
+static uint32_t fused_flags() {
+    static uint32_t v = [] {
+        const char* e = std::getenv("B200FFT_FUSED_NOCOMPUTE");
+        return (e && std::atoi(e) == 1) ? 1u : 0u;
+    }();
+    return v;
+}
+static uint32_t fused_ring_slots(uint32_t per_round, uint64_t bytes_per_transform) {
+    static const uint32_t forced = [] {
+        const char* e = std::getenv("B200FFT_FUSED_W");
+        return e ? (uint32_t)std::atoi(e) : 0u;
+    }();
+    static const uint32_t look = [] {
+        const char* e = std::getenv("B200FFT_FUSED_LOOKAHEAD");
+        const int k = e ? std::atoi(e) : 600;
+        return (uint32_t)(k < 1 ? 1 : k);
+    }();
+    if (forced >= 2) return forced;
+    uint32_t D = (look + per_round - 1) / per_round;
+    if (D < 1) D = 1;
+    uint32_t W = 2 * D;
+    while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W -= 2;  // the ring must stay L2 resident
+    return W;
+}
+
 // The chunked two-pass plans move their tiles with TMA tensor copies (kernels.h, TmaTileKernel) whenever the caller's
 // buffers are 16-byte aligned and the driver exports cuTensorMapEncodeTiled; B200FFT_TMA_TILES=0 selects the LDG/STG
 // passes instead (measured on B200, profiles/r2a: TMA tiles +3..11 % at 2^17..2^20).
@@ -348,6 +399,9 @@ template <> struct HasV1<float, 16384> { static constexpr bool direct = true, ti
 // kind 0: one-pass Smooth plan of pl.len;  kind 1: SmoothFourStep{a x b}
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+// likewise the fused single-launch four-step kernels (b200fft_fused32.cu)
+typedef std::function<bool(const void* in, void* out, void* work, uint64_t batch, rt::stream_t)> FusedFn;
+bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const void* full_tw, FusedFn& fn, uint32_t& W);
 
 template <typename T>
 struct Builder {
@@ -512,6 +566,7 @@ struct Builder {
                 p.discard = 0;
                 p.pf = nullptr;
                 p.pf_bytes = 0;
+                p.ring_w = 0;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -572,6 +627,7 @@ struct Builder {
                 const uint64_t share = (pf && ctas) ? std::min<uint64_t>((pf_total / ctas) & ~15ull, 1u << 20) : 0;
                 p.pf = share ? pf : nullptr;
                 p.pf_bytes = (uint32_t)share;
+                p.ring_w = 0;
                 return rt::launch_tma<KM>(p, ctas, s);
             };
         }
@@ -683,6 +739,97 @@ struct Builder {
         }
         return false;
     }
+    // ---- fused single-launch variant (fused.h: run_fused) ----
+    template <int L1, int L2, bool SW>
+    static bool make_fused_t(b200fft_plan& pl, uint32_t lgN, const C* full_tw, FusedFn& fn, uint32_t& W_out) {
+        if constexpr (sizeof(T) == 4) {
+            using GA = typename FusedGeo<T, L1>::type;
+            using GB = typename FusedGeo<T, L2>::type;
+            using KA = TmaTileKernel<GA, FF, FF, 0, SW>;
+            using KB = TmaTileKernel<GB, JF, FF, 1, SW>;
+            using FK = FusedKernel<KA, KB, FUSED_NG, FUSED_NS>;
+            static_assert(FK::SMEM_BYTES <= MAX_SMEM_PER_CTA, "fused stages must fit one SM");
+            const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2);
+            const C* twa = upload(pl, stage_twiddles<GA>());
+            const C* twb = upload(pl, stage_twiddles<GB>());
+            if (!twa || !twb) return false;
+            if (rt::fused_grid<KA, KB, FUSED_NG, FUSED_NS>() <= 0) return false;
+            const uint32_t TA = (uint32_t)L2 / GA::F, TB = (uint32_t)L1 / GB::F;
+            const uint64_t N = 1ull << lgN;
+            const uint32_t W = fused_ring_slots(TA + TB, N * sizeof(C));
+            W_out = W;
+            const uint64_t ctl_bytes = flow_ctl_bytes(W);
+            fn = [=](const void* in_v, void* out_v, void* work, uint64_t batch, rt::stream_t s) {
+                const C* in = (const C*)in_v;
+                C* out = (C*)out_v;
+                // segments keep the ticket count inside 32 bits and the slab index of the tensor maps inside 31
+                const uint64_t seg = std::max<uint64_t>(1, std::min<uint64_t>(1ull << 24, ((1ull << 30) / (TA + TB))));
+                C* ring = (C*)((char*)work + ctl_bytes);
+                for (uint64_t b0 = 0; b0 < batch; b0 += seg) {
+                    const uint64_t nb = std::min(seg, batch - b0);
+                    typename FK::Params p;
+                    std::memset(&p, 0, sizeof(p));
+                    if (!rt::make_tile_map(&p.a.map_in, false, in + b0 * N, L2, L1, nb, GA::F, KA::BOX_ROWS) ||
+                        !rt::make_tile_map(&p.a.map_out, false, ring, L2, L1, W, GA::F, KA::BOX_ROWS) ||
+                        !rt::make_tile_map(&p.b.map_out, false, out + b0 * N, L1, L2, nb, GB::F, KB::BOX_ROWS))
+                        return false;
+                    p.a.in = in + b0 * N;
+                    p.a.out = ring;
+                    p.a.tw = twa;
+                    p.a.n_fft = nb << lg2;
+                    p.a.lgN = lgN;
+                    p.a.lg_other = lg2;
+                    p.a.ring_w = W;
+                    p.b.in = ring;
+                    p.b.out = out + b0 * N;
+                    p.b.tw = twb;
+                    p.b.full_tw = full_tw;
+                    p.b.n_fft = nb << lg1;
+                    p.b.lgN = lgN;
+                    p.b.lg_other = lg1;
+                    p.b.discard = use_discard() ? 1u : 0u;
+                    p.b.ring_w = W;
+                    p.ctl = (uint32_t*)work;
+                    p.flags = fused_flags();
+                    if (!make_flow_sched(p.sched, nb, TA, TB, W)) {
+                        rt::g_err = "fused schedule overflow";
+                        return false;
+                    }
+                    if (!rt::launch_fused<KA, KB, FUSED_NG, FUSED_NS>(p, ctl_bytes, s)) return false;
+                }
+                return true;
+            };
+            return true;
+        } else {
+            (void)pl; (void)lgN; (void)full_tw; (void)fn; (void)W_out;
+            return false;
+        }
+    }
+    template <int L1>
+    static bool make_fused_l1(b200fft_plan& pl, uint32_t L2, uint32_t lgN, const C* tw, FusedFn& fn, uint32_t& W) {
+        const bool sw = pl.direction != 0;
+        if (L2 == (uint32_t)L1) return sw ? make_fused_t<L1, L1, true>(pl, lgN, tw, fn, W) : make_fused_t<L1, L1, false>(pl, lgN, tw, fn, W);
+        if constexpr (2 * L1 <= (int)TILE_MAX) {
+            if (L2 == 2u * L1)
+                return sw ? make_fused_t<L1, 2 * L1, true>(pl, lgN, tw, fn, W) : make_fused_t<L1, 2 * L1, false>(pl, lgN, tw, fn, W);
+        }
+        return false;
+    }
+    static bool make_fused_rt(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const C* tw, FusedFn& fn, uint32_t& W) {
+        if constexpr (sizeof(T) == 4) return build_fused_f32(pl, L1, L2, lgN, tw, fn, W);
+        return false;
+    }
+    static bool fused_build_here(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const C* tw, FusedFn& fn, uint32_t& W) {
+        switch (L1) {
+            case 128: return make_fused_l1<128>(pl, L2, lgN, tw, fn, W);
+            case 256: return make_fused_l1<256>(pl, L2, lgN, tw, fn, W);
+            case 512: return make_fused_l1<512>(pl, L2, lgN, tw, fn, W);
+            case 1024: return make_fused_l1<1024>(pl, L2, lgN, tw, fn, W);
+            case 2048: return make_fused_l1<2048>(pl, L2, lgN, tw, fn, W);
+            case 4096: return make_fused_l1<4096>(pl, L2, lgN, tw, fn, W);
+        }
+        return false;
+    }
     static bool make_four_step(b200fft_plan& pl, uint32_t lgN) {
         const uint32_t lg1 = lgN / 2, lg2 = lgN - lg1;  // N1 <= N2
         const uint32_t N1 = 1u << lg1, N2 = 1u << lg2;
@@ -716,20 +863,32 @@ struct Builder {
         const bool ok_b = sw ? make_pass_b_rt<true>(pl, N2, lgN, lg1, full_tw, fns) : make_pass_b_rt<false>(pl, N2, lgN, lg1, full_tw, fns);
         if (!ok_a || !ok_b) return false;
         const uint64_t N = 1ull << lgN;
+        // default for f32: one launch of the fused kernel; the chunked launch pairs below stay as the path for buffers
+        // TMA cannot address (not 16-byte aligned) and for f64
+        FusedFn fused;
+        uint32_t fused_w = 0;
+        uint64_t fused_bytes = 0;
+        if (sizeof(T) == 4 && use_fused() && N1 >= 128) {
+            if (!make_fused_rt(pl, N1, N2, lgN, full_tw, fused, fused_w)) return false;
+            fused_bytes = flow_ctl_bytes(fused_w) + (uint64_t)fused_w * N * sizeof(C);
+        }
         const int K = overlap_streams(lgN >= 20 ? 3 : 4);
         // K chunks in flight share the L2 budget
         const uint64_t chunk = std::max<uint64_t>(1, pick_chunk(N * sizeof(C), fns) / (uint64_t)K);
         pl.work_bytes = [=](uint64_t batch) {
             const uint64_t per = std::min(batch, chunk) * N * sizeof(C);
             const uint64_t nchunks = (batch + chunk - 1) / chunk;
-            return per * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
+            return std::max(fused_bytes, per * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1)));
         };
-        pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+        pl.launches = [=](uint64_t batch) { return fused ? (uint64_t)1 : 2 * ((batch + chunk - 1) / chunk); };
         b200fft_plan* self = &pl;
         pl.exec = [=](const ExecCtx& c) {
             const C* in = (const C*)c.in;
             C* out = (C*)c.out;
             C* work = (C*)c.work;
+            if (fused && c.batch < (1ull << 31) &&
+                ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 && (reinterpret_cast<uintptr_t>(work) & 127u) == 0)
+                return fused((const void*)in, (void*)out, c.work, c.batch, c.stream);
             const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
             const int ns = (int)std::min<uint64_t>((uint64_t)(c.max_streams > 0 ? std::min(c.max_streams, K) : K), nchunks);  // streams used
             rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
@@ -783,8 +942,8 @@ struct Builder {
             }
             return ok;
         };
-        pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
-        pl.chunk = chunk;
+        pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + (fused ? ",fused,ring=" + std::to_string(fused_w) : std::string()) + "}";
+        pl.chunk = fused ? fused_w : chunk;
         return true;
     }
 
@@ -1335,6 +1494,11 @@ int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
 #if defined(B2_PART_SMOOTH32)
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here(pl, kind, a, b); }
 #endif
+#if defined(B2_PART_FUSED32)
+bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const void* full_tw, FusedFn& fn, uint32_t& W) {
+    return Builder<float>::fused_build_here(pl, L1, L2, lgN, (const cx<float>*)full_tw, fn, W);
+}
+#endif
 #if defined(B2_PART_SMOOTH64)
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here(pl, kind, a, b); }
 #endif
@@ -1372,6 +1536,10 @@ static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_ou
         if (ws_given) {
             if (ws_bytes < need || !ws)
                 return fail(B200FFT_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+            // the second pass drops consumed workspace lines with discard.global.L2 (128-byte aligned by definition) and
+            // the tiled passes address the workspace through TMA
+            if (reinterpret_cast<uintptr_t>(ws) & 127u)
+                return fail(B200FFT_ERR_INVALID_ARG, "workspace must be 128-byte aligned");
         } else {
             work = rt::malloc_async(need, stream);
             if (!work) return fail(B200FFT_ERR_CUDA, "workspace allocation failed: " + rt::last_error());

@@ -900,7 +900,12 @@ struct TmaTileKernel {
         uint32_t discard;        // ROLE 1: drop the consumed workspace rows from L2 without write-back
         const void* pf;          // ROLE 1, opt-in (B200FFT_PREFETCH=1): input of the NEXT chunk of this stream; every CTA asks
         uint32_t pf_bytes;       //   L2 to fetch its pf_bytes share of it while this pass is still writing output
+        uint32_t ring_w;         // fused single-launch plans (fused.h): the workspace is a ring of ring_w transform slots --
+                                 //   ROLE 0 stores to / ROLE 1 loads from slot (transform mod ring_w); 0 = plain chunk workspace
     };
+    // slab (transform slot) a tile is read from / written to
+    static B2_HD uint32_t zin(const Params& p, uint32_t b) { return (ROLE == 1 && p.ring_w) ? (p.z_in + b) % p.ring_w : p.z_in + b; }
+    static B2_HD uint32_t zout(const Params& p, uint32_t b) { return (ROLE == 0 && p.ring_w) ? (p.z_out + b) % p.ring_w : p.z_out + b; }
     // tables fetched while the tile is in flight (f32, two-stage tiles): the last stage's twiddles and, for pass B,
     // the row's inter-pass twiddles -- the round-1 capture of these kernels had long_scoreboard (table loads issued
     // right before their use) as the top stall
@@ -939,11 +944,18 @@ struct TmaTileKernel {
         if (ROLE == 0) {
             B2_UNROLL
             for (int k = 0; k < NBOX; ++k)
-                tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)(p.z_in + w.b), bar);
+                tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)zin(p, w.b), bar);
         } else {
-            tma::bulk_g2s(buf, p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
+            tma::bulk_g2s(buf, p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
             if (p.pf != nullptr && p.pf_bytes) tma::bulk_prefetch_l2(static_cast<const char*>(p.pf) + (uint64_t)bid * p.pf_bytes, p.pf_bytes);
         }
+    }
+    // one thread: TMA store of the finished dense tile (joins the thread's bulk group; the caller commits / waits)
+    static B2_D void issue_store(const Params& p, uint32_t bid, const cx<T>* buf) {
+        const Where w = where(p, bid);
+        B2_UNROLL
+        for (int k = 0; k < NBOX; ++k)
+            tma::tensor_s2g_3d(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)zout(p, w.b), buf + (size_t)k * BOX_ROWS * G::F);
     }
 #endif
 
@@ -955,11 +967,11 @@ struct TmaTileKernel {
             prefetch(p, bid, tid, r);  // CPU replay (the device does it while the tile is in flight)
             if (tid == 0) {  // CPU replay: the TMA load is a copy
                 if (ROLE == 0) {
-                    const cx<T>* src = p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + w.c0;
+                    const cx<T>* src = p.in + ((uint64_t)zin(p, w.b) << p.lgN) + w.c0;
                     for (int e = 0; e < G::L; ++e)
                         for (int f = 0; f < G::F; ++f) buf[e * G::F + f] = src[((uint64_t)e << p.lg_other) + f];
                 } else {
-                    const cx<T>* src = p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L;
+                    const cx<T>* src = p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L;
                     for (size_t i = 0; i < TILE_ELEMS; ++i) buf[i] = src[i];
                 }
             }
@@ -999,7 +1011,7 @@ struct TmaTileKernel {
             if constexpr (P == 1 && ROLE == 1) {
                 if (p.discard) {  // the tile is in shared memory / registers: its workspace rows are dead
                     const Where w = where(p, bid);
-                    const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)(p.z_in + w.b) << p.lgN) + (uint64_t)w.c0 * G::L);
+                    const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L);
                     for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT) l2_discard_line(base + (size_t)l * 128);
                 }
             }
@@ -1022,13 +1034,11 @@ struct TmaTileKernel {
             if (tid == 0) {
                 const Where w = where(p, bid);
 #if defined(__CUDA_ARCH__)
-                B2_UNROLL
-                for (int k = 0; k < NBOX; ++k)
-                    tma::tensor_s2g_3d(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)(p.z_out + w.b), buf + (size_t)k * BOX_ROWS * G::F);
+                issue_store(p, bid, buf);
                 tma::bulk_commit();
                 tma::bulk_wait_read0();  // shared memory must outlive the store's reads
 #else
-                cx<T>* dst = p.out + ((uint64_t)(p.z_out + w.b) << p.lgN) + w.c0;
+                cx<T>* dst = p.out + ((uint64_t)zout(p, w.b) << p.lgN) + w.c0;
                 for (int e = 0; e < G::L; ++e)
                     for (int f = 0; f < G::F; ++f) dst[((uint64_t)e << p.lg_other) + f] = buf[e * G::F + f];
 #endif

@@ -150,7 +150,7 @@ static bool launch_ex(void (*kern)(P), unsigned grid, unsigned block, size_t sme
 }  // namespace rt
 }  // namespace b2
 
-#include "kernels.h"
+#include "fused.h"
 
 namespace b2 {
 namespace rt {
@@ -432,6 +432,46 @@ static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t c
     if (!memset_async(p.ctl, 0, ctl_bytes, s)) return false;
     const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)grid, (uint64_t)p.sched.total);
     return launch_ex(run_flow<KA, KB>, g, FK::NT, FK::SMEM_BYTES, s, p);
+}
+
+// fused single-launch four-step (fused.h): persistent grid = one CTA per resident slot (queried once per kernel and
+// device); the control block is zeroed on the stream right before the launch (both are graph-capturable)
+template <class KA, class KB, int NG, int NS>
+static int fused_grid() {
+    using FK = FusedKernel<KA, KB, NG, NS>;
+    static std::atomic<int> grid_for_dev[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int grid = grid_for_dev[dev & 63].load(std::memory_order_acquire);
+    if (grid == 0) {
+        if (!check(cudaFuncSetAttribute(run_fused<KA, KB, NG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FK::SMEM_BYTES),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return 0;
+        cudaFuncSetAttribute(run_fused<KA, KB, NG, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
+        int per_sm = 0, sms = 0;
+        if (!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_fused<KA, KB, NG, NS>, FK::NT, FK::SMEM_BYTES),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+            return 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1 || sms < 1) {
+            g_err = "fused kernel does not fit on an SM";
+            return 0;
+        }
+        grid = per_sm * sms;
+        grid_for_dev[dev & 63].store(grid, std::memory_order_release);
+    }
+    return grid;
+}
+template <class KA, class KB, int NG, int NS>
+static bool launch_fused(const typename FusedKernel<KA, KB, NG, NS>::Params& p, uint64_t ctl_bytes, stream_t s) {
+    using FK = FusedKernel<KA, KB, NG, NS>;
+    if (p.sched.total == 0) return true;
+    const int grid = fused_grid<KA, KB, NG, NS>();
+    if (grid <= 0) return false;
+    if (!memset_async(p.ctl, 0, ctl_bytes, s)) return false;
+    const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)grid, (uint64_t)p.sched.total);
+    return launch_ex(run_fused<KA, KB, NG, NS>, g, FK::NT, FK::SMEM_BYTES, s, p);
 }
 
 }  // namespace rt

@@ -66,6 +66,32 @@ B2_D void tensor_s2g_3d(const void* tmap, int x, int y, int z, const void* smem_
 B2_D void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
+// plain arrival (release at CTA scope): publishes this thread's earlier shared-memory writes to the waiters
+B2_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe of a phase
+B2_D bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// full generic <-> async proxy fence (all state spaces): orders a generic-proxy acquire of a flag before the
+// async-proxy (TMA) reads that depend on it, and TMA-written global data before a generic-proxy release
+B2_D void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// all bulk groups of this thread except the newest N have completed (writes performed, not just sources read)
+template <int N> B2_D void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+template <int N> B2_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// named barrier among `count` threads of the CTA (consumer groups of the warp-specialised kernels)
+B2_D void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 B2_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 B2_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 

@@ -21,7 +21,8 @@ static std::string g_err;
 static std::string last_error() { return g_err; }
 static int device_count() { return 1; }
 static bool set_device(int) { return true; }
-static void* dmalloc(size_t n) { return std::malloc(n ? n : 1); }
+// (256-byte aligned like cudaMalloc: the library rejects workspaces that are not 128-byte aligned)
+static void* dmalloc(size_t n) { return std::aligned_alloc(256, (n + 255) / 256 * 256 + 256); }
 static void dfree(void* p) { std::free(p); }
 static bool h2d_sync(void* d, const void* h, size_t n) { std::memcpy(d, h, n); return true; }
 static bool h2d_async(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); return true; }
@@ -29,7 +30,7 @@ static bool d2h_async(void* h, const void* d, size_t n, stream_t) { std::memcpy(
 static bool d2d_async(void* dst, const void* src, size_t n, stream_t) { std::memmove(dst, src, n); return true; }
 static bool set_l2_window(void*, size_t) { return false; }
 static bool memset_async(void* d, int v, size_t n, stream_t) { std::memset(d, v, n); return true; }
-static void* malloc_async(size_t n, stream_t) { return std::malloc(n ? n : 1); }
+static void* malloc_async(size_t n, stream_t) { return dmalloc(n); }
 static void free_async(void* p, stream_t) { std::free(p); }
 static stream_t stream_create() { return (stream_t)1; }
 static void stream_destroy(stream_t) {}
@@ -42,7 +43,7 @@ static bool stream_wait(stream_t, event_t) { return true; }
 }  // namespace rt
 }  // namespace b2
 
-#include "../../rustfft_b200/csrc/kernels.h"
+#include "../../rustfft_b200/csrc/fused.h"
 
 namespace b2 {
 namespace rt {
@@ -152,6 +153,48 @@ static bool launch_flow(const typename FlowKernel<KA, KB>::Params& p, uint64_t c
     }
     for (uint32_t v : seenA) if (v != 1) { g_err = "flow: a pass-A tile did not run exactly once"; return false; }
     for (uint32_t v : seenB) if (v != 1) { g_err = "flow: a pass-B tile did not run exactly once"; return false; }
+    return true;
+}
+
+// fused single-launch four-step (fused.h): same ticket order and counters as the device kernel, one emulated CTA, tiles
+// in ticket order; the store phase of TmaTileKernel (its last phase) stands in for the storer thread
+template <class KA, class KB, int NG, int NS>
+static int fused_grid() { return 148; }
+template <class KA, class KB, int NG, int NS>
+static bool launch_fused(const typename FusedKernel<KA, KB, NG, NS>::Params& p, uint64_t ctl_bytes, stream_t) {
+    using FK = FusedKernel<KA, KB, NG, NS>;
+    using C = cx<typename FK::T>;
+    ++g_launches;
+    std::memset(p.ctl, 0, ctl_bytes);
+    const FlowSched& sc = p.sched;
+    uint32_t* ready = p.ctl + FLOW_CTL_HEAD;
+    uint32_t* freed = ready + sc.ring_w;
+    std::vector<typename KA::Regs> ra((size_t)KA::NT);
+    std::vector<typename KB::Regs> rb((size_t)KB::NT);
+    std::vector<C> smem(FK::STAGE_BYTES / sizeof(C) + 1);
+    std::vector<uint32_t> seenA((size_t)sc.batch * sc.TA, 0), seenB((size_t)sc.batch * sc.TB, 0);
+    for (uint32_t ticket = 0; ticket < sc.total; ++ticket) {
+        int kind;
+        uint32_t t, tile;
+        bool valid;
+        sc.decode(ticket, kind, t, tile, valid);
+        if (!valid) continue;
+        const uint32_t slot = t % sc.ring_w, gen = t / sc.ring_w;
+        std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
+        if (kind == 0) {
+            if (tile >= sc.TA || freed[slot] < gen * sc.TB) { g_err = "fused: pass-A tile scheduled before its ring slot was free"; return false; }
+            ++seenA[(size_t)t * sc.TA + tile];
+            EmuPhases<KA, 0>::run(p.a, t * sc.TA + tile, ra, smem.data());
+            ++ready[slot];
+        } else {
+            if (tile >= sc.TB || ready[slot] < (gen + 1u) * sc.TA) { g_err = "fused: pass-B tile scheduled before pass A finished"; return false; }
+            ++seenB[(size_t)t * sc.TB + tile];
+            EmuPhases<KB, 0>::run(p.b, t * sc.TB + tile, rb, smem.data());
+            ++freed[slot];
+        }
+    }
+    for (uint32_t v : seenA) if (v != 1) { g_err = "fused: a pass-A tile did not run exactly once"; return false; }
+    for (uint32_t v : seenB) if (v != 1) { g_err = "fused: a pass-B tile did not run exactly once"; return false; }
     return true;
 }
 

@@ -115,14 +115,15 @@ def test_power_of_two_plans(planner, n, desc32, desc64):
     f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
     want = desc32 if dtype == np.complex64 else desc64
     # two-pass plans run as the single-launch dataflow kernel: "FourStep{N1xN2,flow,ring=W}"
-    assert f.describe() == want or f.describe().startswith(want[:-1] + ",flow,ring=")
+    # (f32 default: the fused warp-specialised kernel, "FourStep{N1xN2,fused,ring=W}")
+    assert f.describe() == want or f.describe().startswith(want[:-1] + ",flow,ring=") or f.describe().startswith(want[:-1] + ",fused,ring=")
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
 def test_largest_four_step_f32(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     f = check_fft_algorithm(pl, 1 << 20, DIRS[0], np.complex64, control_kind=oracle.PLANNER, chunks=1)
-    assert f.describe() == "FourStep{1024x1024}"
+    assert f.describe().startswith("FourStep{1024x1024")
 
 
 @pytest.mark.parametrize("n,desc", [
@@ -138,29 +139,30 @@ def test_large_convolution_plans(planner, n, desc):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
-def test_chunked_four_step_matches_unchunked(lib):
-    # batch larger than one L2 chunk: 32 MiB / (2^16 * 8 B) = 64 transforms per chunk (the emulation
-    # library is loaded with B200FFT_CHUNK_MB=32, tests/util.py)
+def test_fused_four_step_batches(lib):
+    """f32 two-pass plans run as ONE launch of the fused warp-specialised kernel (fused.h); the replay harness takes the
+    tiles in ticket order and checks that every tile runs exactly once and never before its dependency."""
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 1 << 16, 70
     x = signal(n * batch, np.complex64, seed=5)
     f = pl.plan_fft_forward(n)
-    # B200FFT_CHUNK_MB=32 (fixture) -> 64 transforms of L2 budget, split over the four overlapped streams:
-    # 16 per chunk, four workspaces, ceil(70/16) = 5 chunks x 2 passes
-    assert f.launches(batch) == 10 and f.workspace_bytes(batch) == 4 * 16 * n * 8
+    assert "fused" in f.describe() and f.launches(batch) == 1
     y = x.copy()
     f.process(y)
     for b in (0, 31, 32, 63, 64, 69):
         assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * 16
 
 
-@pytest.mark.parametrize("env", [{"B200FFT_TMA_TILES": "0"}, {"B200FFT_FLOW": "1"}, {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
-                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}, {"B200FFT_NARROW": "1"},
-                                 {"B200FFT_NARROW": "1", "B200FFT_TMA_TILES": "0"}],
-                         ids=["ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead", "narrow-tma-tiles", "narrow-ldg-tiles"])
+@pytest.mark.parametrize("env", [{"B200FFT_FUSED": "0"}, {"B200FFT_FUSED": "0", "B200FFT_TMA_TILES": "0"}, {"B200FFT_FLOW": "1"},
+                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},
+                                 {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}, {"B200FFT_FUSED": "0", "B200FFT_NARROW": "1"},
+                                 {"B200FFT_FUSED": "0", "B200FFT_NARROW": "1", "B200FFT_TMA_TILES": "0"},
+                                 {"B200FFT_FUSED_W": "2"}, {"B200FFT_FUSED_LOOKAHEAD": "40"}, {"B200FFT_FUSED_LOOKAHEAD": "5000"}],
+                         ids=["chunked-tma-tiles", "chunked-ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead", "narrow-tma-tiles",
+                              "narrow-ldg-tiles", "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead"])
 def test_two_pass_variants_in_a_fresh_process(env):
-    """The library reads its switches once per process: the LDG/STG passes (B200FFT_TMA_TILES=0; TMA tiles are the default) and the
-    single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the
+    """The library reads its switches once per process: the chunked launch pairs (B200FFT_FUSED=0; TMA tiles or LDG/STG passes), the
+    fused kernel with other ring sizes, and the single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the
     replay harness also checks that every dataflow tile runs exactly once and never before its dependency."""
     import os
     import subprocess

@@ -195,15 +195,18 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
 @pytest.mark.parametrize("env", [
     {"B200FFT_PIPELINE": "1"},                      # persistent TMA (cp.async.bulk + mbarrier) kernels
     {"B200FFT_RADIX32": "0"},                       # radix <= 16 geometries
-    {"B200FFT_OVERLAP": "0"},                     # multi-pass chunks on one stream
-    {"B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8"},  # many small chunks over four streams
+    {"B200FFT_FUSED": "0"},                         # two-pass plans as chunked launch pairs (TMA tiles) instead of the fused kernel
+    {"B200FFT_FUSED": "0", "B200FFT_OVERLAP": "0"},  # ... chunks on one stream
+    {"B200FFT_FUSED": "0", "B200FFT_STREAMS": "4", "B200FFT_CHUNK_MB": "8"},  # ... many small chunks over four streams
     {"B200FFT_HOST_PIPE": "2"},                     # two-stream host-slice path
-    {"B200FFT_TMA_TILES": "0"},                     # two-pass tiles through LDG/STG instead of TMA tensor copies
-    {"B200FFT_FLOW": "1"},                          # two-pass plans as one launch of the dataflow kernel
+    {"B200FFT_FUSED": "0", "B200FFT_TMA_TILES": "0"},  # two-pass tiles through LDG/STG instead of TMA tensor copies
+    {"B200FFT_FUSED_W": "2"},                       # fused kernel with the smallest ring (every tile waits)
+    {"B200FFT_FUSED_LOOKAHEAD": "40"},              # ... with a short look-ahead
+    {"B200FFT_FUSED_LOOKAHEAD": "5000"},            # ... and a deep one
+    {"B200FFT_FLOW": "1"},                          # two-pass plans as one launch of the (round-1) dataflow kernel
     {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},   # ... with the smallest ring (every tile waits)
-    {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"},  # ... and with a deep look-ahead
-], ids=["tma-pipelined", "radix16", "one-stream", "four-streams-small-chunks", "host-two-stream", "ldg-tiles",
-        "flow", "flow-ring2", "flow-deep"])
+], ids=["tma-pipelined", "radix16", "chunked", "chunked-one-stream", "chunked-four-streams-small-chunks", "host-two-stream", "chunked-ldg-tiles",
+        "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead", "flow", "flow-ring2"])
 def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
     import os
     import subprocess
