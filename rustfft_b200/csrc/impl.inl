@@ -306,10 +306,30 @@ static bool use_fused() {
     }();
     return v;
 }
+// B200FFT_FUSED_HINTS = bit mask of L2 eviction hints on the kernel's TMA copies (1: input loads evict-first, 2: ring loads
+// evict-first, 4: ring stores evict-last, 8: output stores evict-first)
 static uint32_t fused_flags() {
     static uint32_t v = [] {
         const char* e = std::getenv("B200FFT_FUSED_NOCOMPUTE");
-        return (e && std::atoi(e) == 1) ? 1u : 0u;
+        const char* h = std::getenv("B200FFT_FUSED_HINTS");
+        const char* x = std::getenv("B200FFT_FUSED_XFLAGS");  // experiment bits (fused.h), shifted above the hints
+        return ((e && std::atoi(e) == 1) ? 1u : 0u) | ((h ? (uint32_t)std::atoi(h) & 15u : 0u) << 1) | ((x ? (uint32_t)std::atoi(x) : 0u) << 5);
+    }();
+    return v;
+}
+// B200FFT_FUSED_DIRECT=0: finished tiles leave through shared memory + a TMA store (storer thread) instead of 8-byte global
+// stores straight from the registers
+static bool fused_direct() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_FUSED_DIRECT");
+        return !(e && std::atoi(e) == 0);
+    }();
+    return v;
+}
+static bool fused_trace() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_FUSED_TRACE");
+        return e && std::atoi(e) == 1;
     }();
     return v;
 }
@@ -567,6 +587,7 @@ struct Builder {
                 p.pf = nullptr;
                 p.pf_bytes = 0;
                 p.ring_w = 0;
+                p.direct = 0;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -628,6 +649,7 @@ struct Builder {
                 p.pf = share ? pf : nullptr;
                 p.pf_bytes = (uint32_t)share;
                 p.ring_w = 0;
+                p.direct = 0;
                 return rt::launch_tma<KM>(p, ctas, s);
             };
         }
@@ -789,8 +811,13 @@ struct Builder {
                     p.b.lg_other = lg1;
                     p.b.discard = use_discard() ? 1u : 0u;
                     p.b.ring_w = W;
+                    p.a.direct = p.b.direct = fused_direct() ? 1u : 0u;
                     p.ctl = (uint32_t*)work;
                     p.flags = fused_flags();
+                    if (fused_trace()) {  // the stamps live behind the ring (tools/fused_trace.py reads them back)
+                        p.trace = (unsigned long long*)((char*)work + ctl_bytes + (uint64_t)W * N * sizeof(C));
+                        if (!rt::memset_async(p.trace, 0, fused_trace_bytes(), s)) return false;
+                    }
                     if (!make_flow_sched(p.sched, nb, TA, TB, W)) {
                         rt::g_err = "fused schedule overflow";
                         return false;
@@ -870,7 +897,7 @@ struct Builder {
         uint64_t fused_bytes = 0;
         if (sizeof(T) == 4 && use_fused() && N1 >= 128) {
             if (!make_fused_rt(pl, N1, N2, lgN, full_tw, fused, fused_w)) return false;
-            fused_bytes = flow_ctl_bytes(fused_w) + (uint64_t)fused_w * N * sizeof(C);
+            fused_bytes = flow_ctl_bytes(fused_w) + (uint64_t)fused_w * N * sizeof(C) + (fused_trace() ? fused_trace_bytes() : 0);
         }
         const int K = overlap_streams(lgN >= 20 ? 3 : 4);
         // K chunks in flight share the L2 budget

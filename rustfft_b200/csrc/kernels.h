@@ -902,6 +902,9 @@ struct TmaTileKernel {
         uint32_t pf_bytes;       //   L2 to fetch its pf_bytes share of it while this pass is still writing output
         uint32_t ring_w;         // fused single-launch plans (fused.h): the workspace is a ring of ring_w transform slots --
                                  //   ROLE 0 stores to / ROLE 1 loads from slot (transform mod ring_w); 0 = plain chunk workspace
+        uint32_t direct;         // 1: results go from registers straight to global memory (8-byte stores, 64..512-byte runs per
+                                 //   warp instruction) instead of through the shared-memory tile + a TMA store: the tile buffer is
+                                 //   dead after the last exchange read, and an SM's store path is the scarce one (fused.h)
     };
     // slab (transform slot) a tile is read from / written to
     static B2_HD uint32_t zin(const Params& p, uint32_t b) { return (ROLE == 1 && p.ring_w) ? (p.z_in + b) % p.ring_w : p.z_in + b; }
@@ -938,24 +941,36 @@ struct TmaTileKernel {
     }
 
 #if defined(__CUDACC__)
-    static B2_D void issue_load(const Params& p, uint32_t bid, cx<T>* buf, uint64_t* bar) {
+    // pol != 0: an L2 eviction-priority policy (createpolicy) for the tile's lines
+    static B2_D void issue_load(const Params& p, uint32_t bid, cx<T>* buf, uint64_t* bar, unsigned long long pol = 0) {
         const Where w = where(p, bid);
         tma::mbar_arrive_expect_tx(bar, TILE_BYTES);
         if (ROLE == 0) {
             B2_UNROLL
-            for (int k = 0; k < NBOX; ++k)
-                tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)zin(p, w.b), bar);
+            for (int k = 0; k < NBOX; ++k) {
+                if (pol)
+                    tma::tensor_g2s_3d_hint(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)zin(p, w.b), bar, pol);
+                else
+                    tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)zin(p, w.b), bar);
+            }
         } else {
-            tma::bulk_g2s(buf, p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
+            if (pol)
+                tma::bulk_g2s_hint(buf, p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar, pol);
+            else
+                tma::bulk_g2s(buf, p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar);
             if (p.pf != nullptr && p.pf_bytes) tma::bulk_prefetch_l2(static_cast<const char*>(p.pf) + (uint64_t)bid * p.pf_bytes, p.pf_bytes);
         }
     }
     // one thread: TMA store of the finished dense tile (joins the thread's bulk group; the caller commits / waits)
-    static B2_D void issue_store(const Params& p, uint32_t bid, const cx<T>* buf) {
+    static B2_D void issue_store(const Params& p, uint32_t bid, const cx<T>* buf, unsigned long long pol = 0) {
         const Where w = where(p, bid);
         B2_UNROLL
-        for (int k = 0; k < NBOX; ++k)
-            tma::tensor_s2g_3d(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)zout(p, w.b), buf + (size_t)k * BOX_ROWS * G::F);
+        for (int k = 0; k < NBOX; ++k) {
+            if (pol)
+                tma::tensor_s2g_3d_hint(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)zout(p, w.b), buf + (size_t)k * BOX_ROWS * G::F, pol);
+            else
+                tma::tensor_s2g_3d(&p.map_out, (int)(2 * w.c0), k * BOX_ROWS, (int)zout(p, w.b), buf + (size_t)k * BOX_ROWS * G::F);
+        }
     }
 #endif
 
@@ -1020,18 +1035,32 @@ struct TmaTileKernel {
             else
                 Eng::template phase<P - 1>(tid, r.v, buf, p.tw);
             if constexpr (P == NPHASE - 2) {
-                // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
                 int f, j;
                 Eng::out_owner(tid, f, j);
-                cx<T>* dst = buf + (size_t)j * G::F + f;
-                B2_UNROLL
-                for (int q = 0; q < G::E; ++q) dst[(size_t)G::TP * q * G::F] = (ROLE == 1 && SW) ? swap_ri(r.v[q]) : r.v[q];
+                if (p.direct) {
+                    // natural-order results -> global memory: consecutive threads = consecutive f, one run of F elements per row
+                    const Where w = where(p, bid);
+                    cx<T>* dst = p.out + ((uint64_t)zout(p, w.b) << p.lgN) + w.c0 + f;
+                    B2_UNROLL
+                    for (int q = 0; q < G::E; ++q) {
+                        cx<T>* d = dst + ((uint64_t)(j + G::TP * q) << p.lg_other);
+                        if (ROLE == 1)
+                            st_cs(d, SW ? swap_ri(r.v[q]) : r.v[q]);
+                        else
+                            *d = r.v[q];  // plain write-back store: pass B re-reads it from L2
+                    }
+                } else {
+                    // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
+                    cx<T>* dst = buf + (size_t)j * G::F + f;
+                    B2_UNROLL
+                    for (int q = 0; q < G::E; ++q) dst[(size_t)G::TP * q * G::F] = (ROLE == 1 && SW) ? swap_ri(r.v[q]) : r.v[q];
 #if defined(__CUDA_ARCH__)
-                tma::fence_proxy_async();  // generic-proxy writes -> visible to the TMA store below
+                    tma::fence_proxy_async();  // generic-proxy writes -> visible to the TMA store below
 #endif
+                }
             }
         } else {
-            if (tid == 0) {
+            if (tid == 0 && !p.direct) {
                 const Where w = where(p, bid);
 #if defined(__CUDA_ARCH__)
                 issue_store(p, bid, buf);

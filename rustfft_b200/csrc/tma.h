@@ -62,6 +62,25 @@ B2_D void tensor_s2g_3d(const void* tmap, int x, int y, int z, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)
                  : "memory");
 }
+// the same copies with an L2 eviction-priority hint (createpolicy, common.h: l2_evict_first / l2_evict_last)
+B2_D void tensor_g2s_3d_hint(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar, unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "l"(pol)
+        : "memory");
+}
+B2_D void tensor_s2g_3d_hint(const void* tmap, int x, int y, int z, const void* smem_src, unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(tmap),
+                 "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z), "l"(pol)
+                 : "memory");
+}
+B2_D void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
 // ask L2 to fetch a contiguous global range (no destination: a pure prefetch, SASS UBLKPF); bytes a multiple of 16
 B2_D void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");

@@ -13,7 +13,7 @@ HBM = 6487.4
 logs = [int(a) for a in (sys.argv[1].split(",") if len(sys.argv) > 1 else "15,16,17,18,19,20".split(","))]
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("B200FFT_")) or "default"
 pl = rb.FftPlanner(np.complex64)
-total = 1 << 30
+total = 1 << int(os.environ.get('AB_TOTAL_LOG2', '30'))
 x = torch.empty(total, dtype=torch.complex64, device="cuda")
 torch.view_as_real(x).uniform_(0, 10)
 y = torch.empty_like(x)
