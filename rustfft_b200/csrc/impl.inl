@@ -297,7 +297,7 @@ static uint32_t flow_ring_slots(uint32_t per_round, uint64_t bytes_per_transform
 
 // Power-of-two two-pass plans (f32) run as ONE launch of the fused warp-specialised kernel (fused.h) whenever the
 // buffers allow TMA; B200FFT_FUSED=0 selects the chunked launch pairs instead.  B200FFT_FUSED_LOOKAHEAD = tickets pass A
-// runs ahead of pass B (default 600 ~ the tiles in flight on 148 SMs), B200FFT_FUSED_W forces the ring slots,
+// runs ahead of pass B (default 1000 > the ~900 tickets in flight or claimed on 148 SMs), B200FFT_FUSED_W forces the ring slots,
 // B200FFT_FUSED_NOCOMPUTE=1 skips the butterflies (memory-pipeline ceiling; results are garbage).
 static bool use_fused() {
     static bool v = [] {
@@ -307,22 +307,24 @@ static bool use_fused() {
     return v;
 }
 // B200FFT_FUSED_HINTS = bit mask of L2 eviction hints on the kernel's TMA copies (1: input loads evict-first, 2: ring loads
-// evict-first, 4: ring stores evict-last, 8: output stores evict-first)
+// evict-first, 4: ring stores evict-last, 8: output stores evict-first); default 15 (measured +3..8 % over no hints)
 static uint32_t fused_flags() {
     static uint32_t v = [] {
         const char* e = std::getenv("B200FFT_FUSED_NOCOMPUTE");
         const char* h = std::getenv("B200FFT_FUSED_HINTS");
         const char* x = std::getenv("B200FFT_FUSED_XFLAGS");  // experiment bits (fused.h), shifted above the hints
-        return ((e && std::atoi(e) == 1) ? 1u : 0u) | ((h ? (uint32_t)std::atoi(h) & 15u : 0u) << 1) | ((x ? (uint32_t)std::atoi(x) : 0u) << 5);
+        return ((e && std::atoi(e) == 1) ? 1u : 0u) | ((h ? (uint32_t)std::atoi(h) & 15u : 15u) << 1) | ((x ? (uint32_t)std::atoi(x) : 0u) << 5);
     }();
     return v;
 }
-// B200FFT_FUSED_DIRECT=0: finished tiles leave through shared memory + a TMA store (storer thread) instead of 8-byte global
-// stores straight from the registers
-static bool fused_direct() {
+// B200FFT_FUSED_TILED=1: tile-major ring (pass A stores from its registers with coalesced 8-byte stores, pass B gathers its rows with a
+// 4-D tensor copy) instead of the [k1][n2] layout of the chunked path (pass A stores its tile with a TMA tensor store, pass B reads
+// contiguous rows).  Measured on B200 (profiles/): slower -- 64 KiB of register->global stores stall a consumer group for ~1.7 us, the TMA
+// store does the same work in the background -- so it is opt-in.
+static bool fused_tiled() {
     static bool v = [] {
-        const char* e = std::getenv("B200FFT_FUSED_DIRECT");
-        return !(e && std::atoi(e) == 0);
+        const char* e = std::getenv("B200FFT_FUSED_TILED");
+        return e && std::atoi(e) == 1;
     }();
     return v;
 }
@@ -340,7 +342,7 @@ static uint32_t fused_ring_slots(uint32_t per_round, uint64_t bytes_per_transfor
     }();
     static const uint32_t look = [] {
         const char* e = std::getenv("B200FFT_FUSED_LOOKAHEAD");
-        const int k = e ? std::atoi(e) : 600;
+        const int k = e ? std::atoi(e) : 1000;
         return (uint32_t)(k < 1 ? 1 : k);
     }();
     if (forced >= 2) return forced;
@@ -587,7 +589,6 @@ struct Builder {
                 p.pf = nullptr;
                 p.pf_bytes = 0;
                 p.ring_w = 0;
-                p.direct = 0;
                 return rt::launch_tma<KM>(p, p.n_fft / G::F, s);
             };
         }
@@ -649,7 +650,6 @@ struct Builder {
                 p.pf = share ? pf : nullptr;
                 p.pf_bytes = (uint32_t)share;
                 p.ring_w = 0;
-                p.direct = 0;
                 return rt::launch_tma<KM>(p, ctas, s);
             };
         }
@@ -762,13 +762,17 @@ struct Builder {
         return false;
     }
     // ---- fused single-launch variant (fused.h: run_fused) ----
-    template <int L1, int L2, bool SW>
+    template <int L1, int L2, bool SW, bool TILED = true>
     static bool make_fused_t(b200fft_plan& pl, uint32_t lgN, const C* full_tw, FusedFn& fn, uint32_t& W_out) {
         if constexpr (sizeof(T) == 4) {
             using GA = typename FusedGeo<T, L1>::type;
             using GB = typename FusedGeo<T, L2>::type;
-            using KA = TmaTileKernel<GA, FF, FF, 0, SW>;
-            using KB = TmaTileKernel<GB, JF, FF, 1, SW>;
+            if constexpr (TILED) {
+                if (!fused_tiled()) return make_fused_t<L1, L2, SW, false>(pl, lgN, full_tw, fn, W_out);
+            }
+            // TILED: tile-major ring -- pass A stores straight from its registers, pass B gathers its rows with one 4-D tensor copy
+            using KA = TmaTileKernel<GA, FF, FF, 0, SW, TILED ? 1 : 0>;
+            using KB = TmaTileKernel<GB, JF, FF, 1, SW, TILED ? GA::F : 0>;
             using FK = FusedKernel<KA, KB, FUSED_NG, FUSED_NS>;
             static_assert(FK::SMEM_BYTES <= MAX_SMEM_PER_CTA, "fused stages must fit one SM");
             const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2);
@@ -792,8 +796,10 @@ struct Builder {
                     typename FK::Params p;
                     std::memset(&p, 0, sizeof(p));
                     if (!rt::make_tile_map(&p.a.map_in, false, in + b0 * N, L2, L1, nb, GA::F, KA::BOX_ROWS) ||
-                        !rt::make_tile_map(&p.a.map_out, false, ring, L2, L1, W, GA::F, KA::BOX_ROWS) ||
                         !rt::make_tile_map(&p.b.map_out, false, out + b0 * N, L1, L2, nb, GB::F, KB::BOX_ROWS))
+                        return false;
+                    if (TILED ? !rt::make_ring_map(&p.b.map_in, ring, GA::F, L1, TA, W, GB::F, KB::TBOX)
+                              : !rt::make_tile_map(&p.a.map_out, false, ring, L2, L1, W, GA::F, KA::BOX_ROWS))
                         return false;
                     p.a.in = in + b0 * N;
                     p.a.out = ring;
@@ -811,7 +817,6 @@ struct Builder {
                     p.b.lg_other = lg1;
                     p.b.discard = use_discard() ? 1u : 0u;
                     p.b.ring_w = W;
-                    p.a.direct = p.b.direct = fused_direct() ? 1u : 0u;
                     p.ctl = (uint32_t*)work;
                     p.flags = fused_flags();
                     if (fused_trace()) {  // the stamps live behind the ring (tools/fused_trace.py reads them back)

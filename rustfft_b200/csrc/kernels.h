@@ -869,7 +869,13 @@ template <class G> struct RL_last_pow2 {
     static constexpr int R = G::RL::get(G::NS - 1);
     static constexpr bool value = R >= 8 && (R & (R - 1)) == 0;
 };
-template <class G, Map M0, Map M1, int ROLE, bool SW>
+// TILED (fused.h): the workspace ring is TILE-MAJOR -- transform slot = TA dense pass-A tiles [tile][k1][f], 64 KiB each.
+//   ROLE 0, TILED != 0: the results go from the registers straight to the ring with fully coalesced 8-byte stores (the
+//       dense tile IS the memory layout), so the shared-memory buffer is dead after the last exchange read and pass-A tiles
+//       never touch the TMA store path (49 GB/s per SM, measured: the scarce resource of the fused kernel);
+//   ROLE 1, TILED = F of pass A: the tile (F rows x L columns) is gathered by one 4-D tensor copy [all TA tiles][F rows]
+//       [FO columns] and lands as [tile][row][column-in-tile]; phase 0 reads it with that index map.
+template <class G, Map M0, Map M1, int ROLE, bool SW, int TILED = 0>
 struct TmaTileKernel {
     using T = typename G::T;
     using Eng = Engine<G, M0, M1>;
@@ -902,10 +908,23 @@ struct TmaTileKernel {
         uint32_t pf_bytes;       //   L2 to fetch its pf_bytes share of it while this pass is still writing output
         uint32_t ring_w;         // fused single-launch plans (fused.h): the workspace is a ring of ring_w transform slots --
                                  //   ROLE 0 stores to / ROLE 1 loads from slot (transform mod ring_w); 0 = plain chunk workspace
-        uint32_t direct;         // 1: results go from registers straight to global memory (8-byte stores, 64..512-byte runs per
-                                 //   warp instruction) instead of through the shared-memory tile + a TMA store: the tile buffer is
-                                 //   dead after the last exchange read, and an SM's store path is the scarce one (fused.h)
     };
+    static constexpr bool DIRECT_OUT = (ROLE == 0 && TILED != 0);  // registers -> tile-major ring
+    static constexpr int FO = (ROLE == 1 && TILED > 0) ? TILED : 1;  // ROLE 1: columns per pass-A tile
+    static constexpr int TA = G::L / FO;                             // ROLE 1: pass-A tiles per transform
+    static constexpr int TBOX = TA < 256 ? TA : 256;                 // tiles per tensor copy
+    static constexpr bool TILED_IN = (ROLE == 1 && TILED > 0);
+    static_assert(!TILED_IN || (G::L % FO == 0 && TA % TBOX == 0), "tile-major ring geometry");
+    // index of element (row f, column n2 = j + TP q) inside the gathered tile = base(f, j) + tiled_off(q)
+    static B2_HD int tiled_base(int f, int j) {
+        if constexpr (G::TP % FO == 0) return ((j / FO) * G::F + f) * FO + (j % FO);
+        else return f * FO + j;
+    }
+    static constexpr int tiled_off(int q) {
+        if (G::TP % FO == 0) return q * G::TP * G::F;
+        return ((G::TP * q) / FO) * G::F * FO + (G::TP * q) % FO;
+    }
+    static_assert(!TILED_IN || G::TP % FO == 0 || FO % G::TP == 0, "powers of two");
     // slab (transform slot) a tile is read from / written to
     static B2_HD uint32_t zin(const Params& p, uint32_t b) { return (ROLE == 1 && p.ring_w) ? (p.z_in + b) % p.ring_w : p.z_in + b; }
     static B2_HD uint32_t zout(const Params& p, uint32_t b) { return (ROLE == 0 && p.ring_w) ? (p.z_out + b) % p.ring_w : p.z_out + b; }
@@ -953,6 +972,14 @@ struct TmaTileKernel {
                 else
                     tma::tensor_g2s_3d(buf + (size_t)k * BOX_ROWS * G::F, &p.map_in, (int)(2 * w.c0), k * BOX_ROWS, (int)zin(p, w.b), bar);
             }
+        } else if constexpr (TILED_IN) {
+            B2_UNROLL
+            for (int k = 0; k < TA / TBOX; ++k) {
+                if (pol)
+                    tma::tensor_g2s_4d_hint(buf + (size_t)k * TBOX * G::F * FO, &p.map_in, 0, (int)w.c0, k * TBOX, (int)zin(p, w.b), bar, pol);
+                else
+                    tma::tensor_g2s_4d(buf + (size_t)k * TBOX * G::F * FO, &p.map_in, 0, (int)w.c0, k * TBOX, (int)zin(p, w.b), bar);
+            }
         } else {
             if (pol)
                 tma::bulk_g2s_hint(buf, p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L, TILE_BYTES, bar, pol);
@@ -985,6 +1012,11 @@ struct TmaTileKernel {
                     const cx<T>* src = p.in + ((uint64_t)zin(p, w.b) << p.lgN) + w.c0;
                     for (int e = 0; e < G::L; ++e)
                         for (int f = 0; f < G::F; ++f) buf[e * G::F + f] = src[((uint64_t)e << p.lg_other) + f];
+                } else if constexpr (TILED_IN) {
+                    const cx<T>* src = p.in + ((uint64_t)zin(p, w.b) << p.lgN);
+                    for (int t = 0; t < TA; ++t)
+                        for (int f = 0; f < G::F; ++f)
+                            for (int c = 0; c < FO; ++c) buf[((size_t)t * G::F + f) * FO + c] = src[(size_t)t * TILE_ELEMS + (size_t)(w.c0 + f) * FO + c];
                 } else {
                     const cx<T>* src = p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L;
                     for (size_t i = 0; i < TILE_ELEMS; ++i) buf[i] = src[i];
@@ -1001,7 +1033,10 @@ struct TmaTileKernel {
                     r.v[q] = SW ? swap_ri(v) : v;
                 }
             } else {
-                const cx<T>* src = buf + (size_t)f * G::L + j;
+                // element (row f, column j + TP q): row-major tile, or [pass-A tile][row][column-in-tile] when gathered from the
+                // tile-major ring
+                const cx<T>* src = TILED_IN ? buf + tiled_base(f, j) : buf + (size_t)f * G::L + j;
+                auto at = [&](int q) -> cx<T> { return TILED_IN ? src[tiled_off(q)] : src[G::TP * q]; };
                 const cx<T>* t = p.full_tw + (uint64_t)(w.c0 + f) * G::L + j;
 #if defined(B2_TWROW_FEW)
                 if constexpr (sizeof(T) == 4) {
@@ -1012,22 +1047,33 @@ struct TmaTileKernel {
                     B2_UNROLL
                     for (int q = 3; q < G::E; ++q)
                         if (q & (q - 1)) wq[q] = cmul(wq[hibit(q)], wq[q - hibit(q)]);
-                    r.v[0] = cmul(src[0], a);
+                    r.v[0] = cmul(at(0), a);
                     B2_UNROLL
-                    for (int q = 1; q < G::E; ++q) r.v[q] = cmul(src[G::TP * q], cmul(a, wq[q]));
+                    for (int q = 1; q < G::E; ++q) r.v[q] = cmul(at(q), cmul(a, wq[q]));
                 } else
 #endif
                 {
                     B2_UNROLL
-                    for (int q = 0; q < G::E; ++q) r.v[q] = cmul(src[G::TP * q], ldg_stream(t + G::TP * q));
+                    for (int q = 0; q < G::E; ++q) r.v[q] = cmul(at(q), ldg_stream(t + G::TP * q));
                 }
             }
         } else if constexpr (P < NPHASE - 1) {
             if constexpr (P == 1 && ROLE == 1) {
                 if (p.discard) {  // the tile is in shared memory / registers: its workspace rows are dead
                     const Where w = where(p, bid);
-                    const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L);
-                    for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT) l2_discard_line(base + (size_t)l * 128);
+                    if constexpr (TILED_IN) {
+                        // TA chunks of F rows x FO columns (contiguous), one per pass-A tile; whole 128-byte lines only
+                        constexpr uint32_t CHUNK = (uint32_t)(G::F * FO * sizeof(cx<T>));
+                        if constexpr (CHUNK % 128 == 0) {
+                            constexpr uint32_t LPC = CHUNK / 128;
+                            const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * FO);
+                            for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT)
+                                l2_discard_line(base + (size_t)(l / LPC) * TILE_BYTES + (size_t)(l % LPC) * 128);
+                        }
+                    } else {
+                        const char* base = reinterpret_cast<const char*>(p.in + ((uint64_t)zin(p, w.b) << p.lgN) + (uint64_t)w.c0 * G::L);
+                        for (uint32_t l = (uint32_t)tid; l < TILE_BYTES / 128; l += (uint32_t)G::NT) l2_discard_line(base + (size_t)l * 128);
+                    }
                 }
             }
             if constexpr (P == NPHASE - 2 && PRE)
@@ -1037,18 +1083,13 @@ struct TmaTileKernel {
             if constexpr (P == NPHASE - 2) {
                 int f, j;
                 Eng::out_owner(tid, f, j);
-                if (p.direct) {
-                    // natural-order results -> global memory: consecutive threads = consecutive f, one run of F elements per row
+                if constexpr (DIRECT_OUT) {
+                    // natural-order results -> the tile-major ring: the dense tile [row][f] is the memory layout, consecutive
+                    // threads = consecutive f then consecutive rows, i.e. every warp instruction writes 256 contiguous bytes
                     const Where w = where(p, bid);
-                    cx<T>* dst = p.out + ((uint64_t)zout(p, w.b) << p.lgN) + w.c0 + f;
+                    cx<T>* dst = p.out + ((uint64_t)zout(p, w.b) << p.lgN) + (size_t)(w.c0 / G::F) * TILE_ELEMS + (size_t)j * G::F + f;
                     B2_UNROLL
-                    for (int q = 0; q < G::E; ++q) {
-                        cx<T>* d = dst + ((uint64_t)(j + G::TP * q) << p.lg_other);
-                        if (ROLE == 1)
-                            st_cs(d, SW ? swap_ri(r.v[q]) : r.v[q]);
-                        else
-                            *d = r.v[q];  // plain write-back store: pass B re-reads it from L2
-                    }
+                    for (int q = 0; q < G::E; ++q) dst[(size_t)G::TP * q * G::F] = r.v[q];  // write-back stores: pass B re-reads them from L2
                 } else {
                     // natural-order results -> dense output tile (the barrier before this phase ended all reads of buf)
                     cx<T>* dst = buf + (size_t)j * G::F + f;
@@ -1060,7 +1101,7 @@ struct TmaTileKernel {
                 }
             }
         } else {
-            if (tid == 0 && !p.direct) {
+            if (tid == 0 && !DIRECT_OUT) {
                 const Where w = where(p, bid);
 #if defined(__CUDA_ARCH__)
                 issue_store(p, bid, buf);

@@ -350,6 +350,27 @@ static bool make_tile_map(TMap* out, bool f64, const void* base, uint64_t inner_
     }
     return true;
 }
+// the tile-major ring of the fused plans as a 4-D tensor [slot][pass-A tile][row k1][fo columns]: box = all (<= 256) tiles x
+// box_rows rows x fo columns -- the rows of one pass-B tile, gathered from every pass-A tile of the transform
+static bool make_ring_map(TMap* out, const void* base, uint32_t fo, uint64_t rows, uint64_t tiles, uint64_t slots, uint32_t box_rows,
+                          uint32_t box_tiles) {
+    encode_tiled_fn fn = encode_tiled();
+    if (!fn) {
+        g_err = "cuTensorMapEncodeTiled is not available";
+        return false;
+    }
+    const cuuint64_t dims[4] = {2ull * fo, rows, tiles, slots};
+    const cuuint64_t strides[3] = {2ull * fo * 4, 2ull * fo * 4 * rows, 2ull * fo * 4 * rows * tiles};
+    const cuuint32_t box[4] = {2 * fo, box_rows, box_tiles, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_err = "cuTensorMapEncodeTiled (ring) failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
 template <class KT>
 static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) {
     if (ctas == 0) return true;

@@ -57,6 +57,19 @@ B2_D void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, u
                  "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
                  : "memory");
 }
+B2_D void tensor_g2s_4d(void* smem_dst, const void* tmap, int x, int y, int z, int w, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
+}
+B2_D void tensor_g2s_4d_hint(void* smem_dst, const void* tmap, int x, int y, int z, int w, uint64_t* bar, unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w), "l"(pol)
+        : "memory");
+}
 B2_D void tensor_s2g_3d(const void* tmap, int x, int y, int z, const void* smem_src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
                  "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)

@@ -110,6 +110,10 @@ static bool make_tile_map(TMap* out, bool, const void*, uint64_t, uint64_t, uint
     std::memset(out, 0, sizeof(*out));
     return true;
 }
+static bool make_ring_map(TMap* out, const void*, uint32_t, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t) {
+    std::memset(out, 0, sizeof(*out));
+    return true;
+}
 template <class KT>
 static bool launch_tma(const typename KT::Params& p, uint64_t ctas, stream_t s) { return launch<KT>(p, ctas, s); }
 

@@ -1,16 +1,13 @@
 #!/bin/bash
-OUT=gpurun_out/s7
+OUT=gpurun_out/s10
 mkdir -p $OUT
 export PYTHONPATH=$PWD:$PWD/tests
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "config2_power or up_to_2_24 or ragged or device_path" > $OUT/pytest_quick.log 2>&1
-echo "pytest quick rc=$?" >> $OUT/pytest_quick.log
-tail -n 3 $OUT/pytest_quick.log
-for v in "" "B200FFT_FUSED_XFLAGS=1" "B200FFT_FUSED_DIRECT=0 B200FFT_FUSED_XFLAGS=1" "B200FFT_FUSED_NOCOMPUTE=1" "B200FFT_FUSED_XFLAGS=1 B200FFT_FUSED_LOOKAHEAD=800" "B200FFT_FUSED_XFLAGS=1 B200FFT_FUSED_LOOKAHEAD=1000" "B200FFT_FUSED_XFLAGS=1 B200FFT_FUSED_HINTS=3"; do
+for v in "" "B200FFT_FUSED_XFLAGS=2" "B200FFT_FUSED_LOOKAHEAD=800" "B200FFT_FUSED_HINTS=9"; do
   env $v timeout 200 python tools/ab_two_pass.py 15,16,17,18,19,20 >> $OUT/ab.log 2>&1
 done
 grep SUMMARY $OUT/ab.log
-export B200FFT_FUSED_TRACE=1 B200FFT_FUSED_XFLAGS=1
-for lg in 20 16; do
-  timeout 120 python tools/fused_trace.py $lg > $OUT/trace_$lg.txt 2>&1
-  tail -n 7 $OUT/trace_$lg.txt
-done
+timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+tail -n 5 $OUT/pytest_gpu.log
+timeout 600 python bench.py --no-cpu > $OUT/bench.json 2> $OUT/bench.err
+tail -c 3000 $OUT/bench.json
