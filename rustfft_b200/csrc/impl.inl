@@ -328,6 +328,15 @@ static bool fused_tiled() {
     }();
     return v;
 }
+// B200FFT_FUSED_TW2=1: two-level inter-pass twiddles from 16 KiB of L1-resident tables instead of the N-entry table streamed from L2
+// (measured: no gain -- the table loads are prefetched while the tile is in flight -- and one more rounding; opt-in)
+static bool fused_tw2() {
+    static bool v = [] {
+        const char* e = std::getenv("B200FFT_FUSED_TW2");
+        return e && std::atoi(e) == 1;
+    }();
+    return v;
+}
 static bool fused_trace() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_FUSED_TRACE");
@@ -580,6 +589,7 @@ struct Builder {
                 p.out = work;
                 p.tw = tw;
                 p.full_tw = nullptr;
+                p.tw_lo = p.tw_hi = nullptr;
                 p.n_fft = nb << lg2;
                 p.lgN = lgN;
                 p.lg_other = lg2;
@@ -639,6 +649,7 @@ struct Builder {
                 p.out = out;
                 p.tw = tw;
                 p.full_tw = full_tw;
+                p.tw_lo = p.tw_hi = nullptr;
                 p.n_fft = nb << lg1;
                 p.lgN = lgN;
                 p.lg_other = lg1;
@@ -779,6 +790,17 @@ struct Builder {
             const C* twa = upload(pl, stage_twiddles<GA>());
             const C* twb = upload(pl, stage_twiddles<GB>());
             if (!twa || !twb) return false;
+            // optional two-level inter-pass twiddles (B200FFT_FUSED_TW2=1)
+            const C *tw_lo = nullptr, *tw_hi = nullptr;
+            if (fused_tw2() && KB::PRE) {
+                const uint64_t Nn = 1ull << lgN;
+                std::vector<C> lo(1024), hi((size_t)(Nn >> 10));
+                for (uint64_t i = 0; i < 1024; ++i) lo[(size_t)i] = hm::twiddle<T>(i, Nn);
+                for (uint64_t h = 0; h < (Nn >> 10); ++h) hi[(size_t)h] = hm::twiddle<T>(h, Nn >> 10);
+                tw_lo = upload(pl, lo);
+                tw_hi = upload(pl, hi);
+                if (!tw_lo || !tw_hi) return false;
+            }
             if (rt::fused_grid<KA, KB, FUSED_NG, FUSED_NS>() <= 0) return false;
             const uint32_t TA = (uint32_t)L2 / GA::F, TB = (uint32_t)L1 / GB::F;
             const uint64_t N = 1ull << lgN;
@@ -812,6 +834,8 @@ struct Builder {
                     p.b.out = out + b0 * N;
                     p.b.tw = twb;
                     p.b.full_tw = full_tw;
+                    p.b.tw_lo = tw_lo;
+                    p.b.tw_hi = tw_hi;
                     p.b.n_fft = nb << lg1;
                     p.b.lgN = lgN;
                     p.b.lg_other = lg1;

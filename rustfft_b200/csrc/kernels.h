@@ -906,6 +906,8 @@ struct TmaTileKernel {
         uint32_t discard;        // ROLE 1: drop the consumed workspace rows from L2 without write-back
         const void* pf;          // ROLE 1, opt-in (B200FFT_PREFETCH=1): input of the NEXT chunk of this stream; every CTA asks
         uint32_t pf_bytes;       //   L2 to fetch its pf_bytes share of it while this pass is still writing output
+        const cx<T>* tw_lo;      // ROLE 1, optional: two-level inter-pass twiddles W_N^m = tw_hi[m >> 10] * tw_lo[m & 1023] (tw_lo[i] =
+        const cx<T>* tw_hi;      //   W_N^i, tw_hi[h] = W_N^(1024 h)): 16 KiB that stay in L1 instead of an N-entry table streamed from L2
         uint32_t ring_w;         // fused single-launch plans (fused.h): the workspace is a ring of ring_w transform slots --
                                  //   ROLE 0 stores to / ROLE 1 loads from slot (transform mod ring_w); 0 = plain chunk workspace
     };
@@ -947,10 +949,22 @@ struct TmaTileKernel {
             if (ROLE == 1) {
                 const Where w = where(p, bid);
                 Eng::template owner<0>(tid, f, j);
-                const cx<T>* t = p.full_tw + (uint64_t)(w.c0 + f) * G::L;
-                r.rw[0] = ldg_stream(t + j);
-                B2_UNROLL
-                for (int l = 0; l < LGE; ++l) r.rw[l + 1] = ldg_stream(t + G::TP * (1 << l));
+                if (p.tw_lo != nullptr) {
+                    // W_N^(k1 x) from two L1-resident tables (one more rounding than the full table, no trip to L2)
+                    const uint32_t k1 = w.c0 + (uint32_t)f, mask = (1u << p.lgN) - 1u;
+                    auto tw2 = [&](uint32_t x) -> cx<T> {
+                        const uint32_t m = (k1 * x) & mask;
+                        return cmul(ldg(p.tw_hi + (m >> 10)), ldg(p.tw_lo + (m & 1023u)));
+                    };
+                    r.rw[0] = tw2((uint32_t)j);
+                    B2_UNROLL
+                    for (int l = 0; l < LGE; ++l) r.rw[l + 1] = tw2((uint32_t)(G::TP * (1 << l)));
+                } else {
+                    const cx<T>* t = p.full_tw + (uint64_t)(w.c0 + f) * G::L;
+                    r.rw[0] = ldg_stream(t + j);
+                    B2_UNROLL
+                    for (int l = 0; l < LGE; ++l) r.rw[l + 1] = ldg_stream(t + G::TP * (1 << l));
+                }
             }
         }
     }
