@@ -50,20 +50,78 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_sample(threads: int, reps: int = 8):
-    """Bounded sample of the sweep on the host: per size, 2^24 complex elements (128 MiB), `reps` passes."""
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+_cpu_buf = None
+
+
+def cpu_sample(threads: int, min_reps: int = 5, target_s: float = 0.25, logs=None):
+    """One pass of the SAME workload on the host: every N in 2^10..2^20 with batch = 4096 (BASELINE configs[1]), in place, f32,
+    through the C++ port of RustFFT's scalar planner path -- `threads` pinned workers created once per size outside the timed
+    passes, each with its own contiguous slice of the batch (examples/concurrency.rs), >= `min_reps` separately timed passes per
+    size (more for the small sizes, to ~target_s), median pass per size.  Returns (GFLOP/s of the sweep, seconds of timed CPU
+    work, per-size rows)."""
+    import numpy as np
+
     import oracle
 
-    total_f, total_t, per = 0.0, 0.0, []
-    for lg in LOGS:
+    global _cpu_buf
+    logs = logs or LOGS
+    batch = BATCH
+    if _cpu_buf is None:
+        while True:
+            try:
+                _cpu_buf = np.empty(batch << max(logs), dtype=np.complex64)  # untouched pages: the workers first-touch their slices
+                break
+            except MemoryError:  # pragma: no cover  (a box without 32 GiB to spare: shrink the batch and say so)
+                batch //= 2
+    batch = _cpu_buf.size >> max(logs)
+    total_f, total_t, spent, per = 0.0, 0.0, 0.0, []
+    for lg in logs:
         n = 1 << lg
-        batch = max(threads, (1 << 24) // n)
-        t = oracle.time_f32(n, batch, threads, reps)
-        f = flops(n, batch) * reps
-        per.append({"log2n": lg, "batch": batch, "gflops": round(f / t / 1e9, 2)})
+        f = flops(n, batch)
+        reps = int(min(200, max(min_reps, math.ceil(target_s / (f / 1.5e11)))))
+        ts = sorted(oracle.bench_f32(n, batch, threads, reps, _cpu_buf))
+        med = ts[len(ts) // 2]
+        per.append({"log2n": lg, "batch": batch, "reps": reps, "gflops": round(f / med / 1e9, 2), "gflops_best": round(f / ts[0] / 1e9, 2),
+                    "gflops_per_core": round(f / med / 1e9 / threads, 3)})
         total_f += f
-        total_t += t
-    return total_f / total_t / 1e9, total_t, per
+        total_t += med
+        spent += sum(ts)
+    return total_f / total_t / 1e9, spent, per
+
+
+def scipy_sample(threads: int, logs=None):
+    """Second CPU comparator (NOT RustFFT): scipy.fft (pocketfft, SIMD over the batch) with workers = all host threads, complex64,
+    batch = min(4096, 2^27 / N) transforms per size, best of 3."""
+    try:
+        import numpy as np
+        import scipy.fft as sfft
+    except Exception as e:  # pragma: no cover
+        return {"error": f"{type(e).__name__}: {e}"[:120]}
+    logs = logs or LOGS
+    rng = np.random.default_rng(7)
+    total_f, total_t, per = 0.0, 0.0, []
+    for lg in logs:
+        n = 1 << lg
+        batch = max(1, min(BATCH, (1 << 27) // n))
+        x = (rng.random((batch, n), dtype=np.float32) + 1j * rng.random((batch, n), dtype=np.float32)).astype(np.complex64)
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            sfft.fft(x, axis=-1, workers=threads)
+            best = min(best, time.perf_counter() - t0)
+        f = flops(n, batch)
+        per.append({"log2n": lg, "batch": batch, "gflops": round(f / best / 1e9, 2)})
+        total_f += f
+        total_t += best
+    return {"value": round(total_f / total_t / 1e9, 2), "unit": "GFLOP/s", "workers": threads, "what": "scipy.fft.fft complex64 (pocketfft), "
+            "batch = min(4096, 2^27/N) per size, best of 3 -- a vectorised CPU FFT, not RustFFT", "per_size": per}
 
 
 def run_reference(args, rank: int, world: int):
@@ -72,25 +130,30 @@ def run_reference(args, rank: int, world: int):
     import oracle
 
     oracle.build()
-    cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_sample(cores, reps=1)
-    vals, t_all = [], 0.0
+    cores = host_threads()
+    logs = LOGS if not args.logs else [int(x) for x in args.logs.split(",")]
+    for _ in range(min(args.warmup, 1)):  # one untimed pass warms the plans' code and the page tables; every timed pass already has
+        cpu_sample(cores, min_reps=2, target_s=0.0, logs=logs)  # its own warm data (in place, same buffer)
+    vals, t_all, per = [], 0.0, None
     for _ in range(args.steps):
-        g, t, per = cpu_sample(cores)
+        g, t, per = cpu_sample(cores, logs=logs)
         vals.append(g)
         t_all += t
-    value = sum(vals) / len(vals)
-    sample = "per step: every N in 2^10..2^20 with batch = 2^24/N transforms (128 MiB per size), 8 passes each"
+    value = sorted(vals)[len(vals) // 2]
+    step_ms = 1e3 * sum(flops(1 << lg, per[0]["batch"]) for lg in logs) / (value * 1e9)
+    sample = (f"per step: every N in 2^10..2^20 with batch = {per[0]['batch']} (the GPU arm's workload), in place, >= 5 separately timed passes per "
+              "size, median pass; workers created and pinned once per size outside the timed passes")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_all / args.steps, 2),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "f32 forward N=2^10..2^20 (BASELINE configs[1]); reference arm = C++ port of RustFFT's "
-                               "scalar planner path (RustFFT itself needs rustc, absent from the image)",
-                   "per_size": per},
+        "config": {"workload": "BASELINE configs[1]: f32 forward, N=2^10..2^20, batch=4096 per GPU, out of place, "
+                               "device resident", "sizes_log2": logs, "batch_per_gpu": BATCH,
+                   "reference_arm": "C++ port of RustFFT's scalar planner path (oracle/; RustFFT itself needs rustc, absent from the image), "
+                                    "in place on host memory, all host threads", "per_size": per},
         "cpu_baseline": {"value": round(value, 2), "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scipy_fft": scipy_sample(cores, logs),
     }), flush=True)
 
 
@@ -367,7 +430,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_step")
 
-    # ---- e2e: the host-slice trait path from pinned host memory (rank-local), PCIe inside the timing
+    # ---- e2e: the host-slice trait path (rank-local), PCIe inside the timing: pinned host buffers (headline) and pageable ones
     e2e = None
     if not args.no_e2e:
         cap = int(args.e2e_pinned_gib * (1 << 30)) // 8
@@ -376,32 +439,71 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.view_as_real(hin).uniform_(0, 10)
         hin_np, hout_np = hin.numpy(), hout.numpy()
 
-        def e2e_step():
+        def e2e_step(a_np, b_np):
             for lg in logs:
                 n = 1 << lg
                 todo = BATCH
-                per_call = max(1, min(BATCH, hin_np.size // n))
+                per_call = max(1, min(BATCH, a_np.size // n))
                 while todo:
                     nb = min(per_call, todo)
-                    plans[lg].process_outofplace_with_scratch(hin_np[: nb * n], hout_np[: nb * n])
+                    plans[lg].process_outofplace_with_scratch(a_np[: nb * n], b_np[: nb * n])
                     todo -= nb
 
-        e2e_step()  # warm-up (staging allocations, page faults)
-        barrier()
+        def timed_e2e(a_np, b_np, steps):
+            e2e_step(a_np, b_np)  # warm-up (pipeline resources, page faults)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step(a_np, b_np)
+            barrier()
+            sec = (time.perf_counter() - t0) / steps
+            if dist:
+                tt = torch.tensor([sec], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                sec = tt.item()
+            return sec
+
+        e2e_s = timed_e2e(hin_np, hout_np, args.e2e_steps)
+        # the link itself: concurrent H2D + D2H of 1 GiB blocks on two streams (what any host pipeline is bounded by)
+        blk = min(1 << 27, hin.numel())
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        dtmp = torch.empty(blk, dtype=torch.complex64, device=dev)
+        dtmp2 = torch.empty(blk, dtype=torch.complex64, device=dev)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        if dist:
-            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = tt.item()
+        for _ in range(4):
+            with torch.cuda.stream(s1):
+                dtmp.copy_(hin[:blk], non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout[:blk].copy_(dtmp2, non_blocking=True)
+        torch.cuda.synchronize()
+        link = 4 * blk * 8 / (time.perf_counter() - t0) / 1e9
+        del dtmp, dtmp2
+        # pageable caller (what a Rust Vec is): staged through the library's pinned ring by its copy threads
+        pg_in = np.empty(hin_np.size, dtype=np.complex64)
+        pg_in[:] = hin_np
+        pg_out = np.empty_like(pg_in)
+        pg_s = timed_e2e(pg_in, pg_out, 1)
+        del pg_in, pg_out
+        # config 1's GPU twin: one N = 1024 transform through process() (H2D + kernel + D2H + sync), pageable
+        one = (np.random.default_rng(1).random(1024) + 0j).astype(np.complex64)
+        for _ in range(20):
+            plans[10].process(one)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            plans[10].process(one)
+        lat_us = (time.perf_counter() - t0) / 200 * 1e6
+        per_dir = step_bytes / 2 / e2e_s / 1e9
         e2e = {"value": round(step_flops * world / e2e_s / 1e9, 1), "unit": "GFLOP/s",
                "h2d_bytes_per_step": int(step_bytes // 2) * world, "d2h_bytes_per_step": int(step_bytes // 2) * world,
                "ms_per_step": round(e2e_s * 1e3, 1), "steps": args.e2e_steps,
+               "gbs_per_direction": round(per_dir, 1), "link_gbs_per_direction_concurrent": round(link, 1),
+               "frac_of_link": round(per_dir / link, 3),
+               "pageable": {"value": round(step_flops * world / pg_s / 1e9, 1), "unit": "GFLOP/s", "ms_per_step": round(pg_s * 1e3, 1),
+                            "gbs_per_direction": round(step_bytes / 2 / pg_s / 1e9, 1)},
+               "process_latency_us_n1024_batch1": round(lat_us, 1),
                "how": "b200fft_exec_host_outofplace on pinned host buffers (wall clock incl. H2D+D2H), "
-                      f"{args.e2e_pinned_gib} GiB pinned window reused per call"}
+                      f"{args.e2e_pinned_gib} GiB window reused per call; `pageable`: the same from numpy-allocated memory"}
 
     # ---- the other BASELINE configs, device resident, informational (not part of `value`) --------------
     extras = None
@@ -490,12 +592,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         import oracle
 
         oracle.build()
-        cores = os.cpu_count() or 1
-        cpu_sample(cores, reps=1)
-        gcpu, tcpu, _ = cpu_sample(cores, reps=4)
+        cores = host_threads()
+        gcpu, tcpu, per_cpu = cpu_sample(cores, min_reps=5, target_s=0.2, logs=logs)
         cpu = {"value": round(gcpu, 2), "unit": "GFLOP/s", "cores": cores, "kind": "port",
-               "sample": "every N in 2^10..2^20, batch = 2^24/N transforms per size, 4 passes "
-                         f"({tcpu:.1f} s of CPU work); C++ port of RustFFT's scalar planner path, one batch slice per thread"}
+               "sample": f"every N in 2^10..2^20 with batch = {per_cpu[0]['batch']} (the same workload), in place, >= 5 separately timed passes per size, "
+                         f"median pass ({tcpu:.1f} s of timed CPU work); C++ port of RustFFT's scalar planner path, pinned workers, one batch slice each",
+               "per_size": per_cpu}
 
     if rank == 0:
         print(json.dumps({

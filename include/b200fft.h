@@ -79,8 +79,10 @@ int b200fft_plan_describe(const b200fft_plan* plan, char* buf, uint64_t cap);
 /* Kernel launches one exec of `batch` transforms issues (bench.py reports it as gpu_launches). */
 uint64_t b200fft_plan_launches(const b200fft_plan* plan, uint64_t batch);
 
-/* Trait-conformant host paths: pageable host memory owned by the caller, n_complex = batch*len elements.
- * H2D -> kernels -> D2H, chunked and double-buffered through pinned staging buffers; synchronous. */
+/* Trait-conformant host paths: host memory owned by the caller (pageable or pinned), n_complex = batch*len elements;
+ * synchronous.  The batch flows in 64 MiB slices through a three-stage pipeline (copy in | kernels | copy out, one stream each)
+ * over a ring of four device buffers owned by the plan (created on the first call, reused afterwards).  Pinned / registered
+ * memory is copied from and to directly; pageable memory is staged through a pinned ring by a small pool of copy threads. */
 int b200fft_exec_host_inplace(const b200fft_plan* plan, void* buffer, uint64_t n_complex);
 int b200fft_exec_host_outofplace(const b200fft_plan* plan, const void* input, void* output, uint64_t n_complex);
 
@@ -88,7 +90,8 @@ int b200fft_exec_host_outofplace(const b200fft_plan* plan, const void* input, vo
  * d_in == d_out allowed; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
  * Plans that need an intermediate buffer take it from the stream-ordered allocator. */
 int b200fft_exec_device(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream);
-/* Same, with a caller-provided device workspace of at least b200fft_workspace_bytes(plan, batch) bytes. */
+/* Same, with a caller-provided device workspace of at least b200fft_workspace_bytes(plan, batch) bytes, 128-byte aligned
+ * (the passes address it through TMA and drop consumed lines with discard.global.L2; B200FFT_ERR_INVALID_ARG otherwise). */
 uint64_t b200fft_workspace_bytes(const b200fft_plan* plan, uint64_t batch);
 int b200fft_exec_device_ws(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch,
                            void* cuda_stream, void* d_workspace, uint64_t workspace_bytes);

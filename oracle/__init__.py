@@ -45,6 +45,7 @@ def _lib(fast: bool = False):
         lib.oracle_fft_f64.argtypes = [i32, u64, i32, ctypes.c_void_p, u64, i32]
         lib.oracle_time_f32.argtypes = [i32, u64, i32, ctypes.c_void_p, u64, i32, i32]
         lib.oracle_time_f32.restype = ctypes.c_double
+        lib.oracle_bench_f32.argtypes = [i32, u64, u64, i32, i32, ctypes.c_void_p, ctypes.c_void_p]
         lib.oracle_describe_plan.argtypes = [u64, ctypes.c_char_p, u64]
         lib.oracle_modular_exponent.argtypes = [u64, u64, u64]
         lib.oracle_modular_exponent.restype = u64
@@ -89,6 +90,20 @@ def time_f32(n: int, batch: int, threads: int, reps: int = 1, kind: int = PLANNE
     if t < 0:
         raise RuntimeError("oracle_time_f32 failed")
     return t
+
+
+def bench_f32(n: int, batch: int, threads: int, reps: int, buf: np.ndarray = None, kind: int = PLANNER) -> list:
+    """Per-pass seconds of `reps` timed passes over `batch` f32 transforms of length n on `threads` pinned workers (fast build).
+    Workers are created once, first-touch and fill their own slice of `buf` (complex64, >= batch*n elements; allocated
+    uninitialised here when None), and every pass is timed between two barriers -- see oracle_bench_f32."""
+    if buf is None:
+        buf = np.empty(n * batch, dtype=np.complex64)
+    assert buf.dtype == np.complex64 and buf.size >= n * batch
+    times = (ctypes.c_double * reps)()
+    rc = _lib(True).oracle_bench_f32(kind, n, batch, threads, reps, buf.ctypes.data, times)
+    if rc != 0:
+        raise RuntimeError("oracle_bench_f32 failed")
+    return [float(times[i]) for i in range(reps)]
 
 
 def describe_plan(n: int) -> str:

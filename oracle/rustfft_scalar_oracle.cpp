@@ -1173,3 +1173,87 @@ extern "C" double oracle_time_f32(int kind, uint64_t len, int inverse, float* da
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
 }
+
+// ---- honest multi-core timing (bench.py cpu_baseline / --impl reference) --------------------------------------------
+// benches/bench_rustfft.rs:43-54 times `fft.process_with_scratch` on a prepared plan; examples/concurrency.rs:17-29 shares one plan between
+// threads, each with its own buffer.  Here: `nthreads` workers are created ONCE per call, pinned to distinct CPUs of the allowed set,
+// first-touch and fill their own contiguous slice of the batch (so pages live on the worker's NUMA node), and then run `reps` timed
+// passes; every pass is bracketed by a spin barrier and timed separately (times_out[r], seconds).  Between passes (untimed) the slices
+// are rescaled so repeated in-place unnormalised transforms stay finite.
+#include <atomic>
+#include <sched.h>
+namespace {
+struct SpinBarrier {
+    std::atomic<int> count{0};
+    std::atomic<int> sense{0};
+    int n;
+    explicit SpinBarrier(int n_) : n(n_) {}
+    void wait(int& local) {
+        local ^= 1;
+        if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(local, std::memory_order_release);
+        } else {
+            while (sense.load(std::memory_order_acquire) != local) __builtin_ia32_pause();
+        }
+    }
+};
+}  // namespace
+extern "C" int oracle_bench_f32(int kind, uint64_t len, uint64_t batch, int nthreads, int reps, float* data, double* times_out) {
+    if (len == 0 || batch == 0 || reps < 1 || !data || !times_out) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > batch) nthreads = (int)batch;
+    std::vector<int> cpus;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) cpus.push_back(c);
+    Cx<float>* x = reinterpret_cast<Cx<float>*>(data);
+    // only the workers take part in the barriers (a spinning main thread would steal a pinned worker's CPU); every worker stamps
+    // its own start and end of a pass, pass time = last end - first start
+    SpinBarrier bar(nthreads);
+    typedef std::chrono::steady_clock clk;
+    std::vector<clk::time_point> t_start((size_t)nthreads * reps), t_end((size_t)nthreads * reps);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t]() {
+            if (!cpus.empty()) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[(size_t)t % cpus.size()], &one);
+                sched_setaffinity(0, sizeof(one), &one);
+            }
+            const usize b0 = (usize)batch * (usize)t / (usize)nthreads, b1 = (usize)batch * (usize)(t + 1) / (usize)nthreads;
+            NodeP<float> plan = build<float>(kind, (usize)len, false);
+            uint32_t s = 0x9E3779B9u * (uint32_t)(t + 1);
+            for (usize i = b0 * (usize)len; i < b1 * (usize)len; ++i) {  // first touch + fill: U[0, 10)
+                s = s * 1664525u + 1013904223u;
+                const float re = (float)(s >> 8) * (10.0f / 16777216.0f);
+                s = s * 1664525u + 1013904223u;
+                x[i] = Cx<float>{re, (float)(s >> 8) * (10.0f / 16777216.0f)};
+            }
+            const float scale = 1.0f / std::sqrt((float)len);
+            int local = 0;
+            for (int r = 0; r < reps; ++r) {
+                if (r > 0)
+                    for (usize i = b0 * (usize)len; i < b1 * (usize)len; ++i) x[i] = Cx<float>{x[i].re * scale, x[i].im * scale};
+                bar.wait(local);  // start of the timed pass
+                t_start[(size_t)r * nthreads + t] = clk::now();
+                for (usize b = b0; b < b1; ++b) plan->run(x + b * (usize)len);
+                t_end[(size_t)r * nthreads + t] = clk::now();
+                bar.wait(local);  // end of the timed pass
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int r = 0; r < reps; ++r) {
+        clk::time_point a = t_start[(size_t)r * nthreads], b = t_end[(size_t)r * nthreads];
+        for (int t = 1; t < nthreads; ++t) {
+            if (t_start[(size_t)r * nthreads + t] < a) a = t_start[(size_t)r * nthreads + t];
+            if (t_end[(size_t)r * nthreads + t] > b) b = t_end[(size_t)r * nthreads + t];
+        }
+        times_out[r] = std::chrono::duration<double>(b - a).count();
+    }
+    return 0;
+}

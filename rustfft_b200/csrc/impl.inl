@@ -15,7 +15,9 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -153,6 +155,36 @@ struct ExecCtx {
     int max_streams;  // 0 = plan default; the host-slice pipeline passes 1 (it is PCIe bound and already staged)
 };
 
+// resources of one host-slice pipeline (exec_host_impl); grow-only, owned by a plan
+struct HostPipe {
+    static constexpr int NB = 4;  // ring slots
+    rt::stream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    rt::event_t ev_in[NB] = {}, ev_k[NB] = {}, ev_out[NB] = {};
+    void* dbuf[NB] = {};
+    uint64_t dbuf_bytes = 0;
+    void* pin_in[NB] = {};   // pinned staging for pageable callers
+    void* pin_out[NB] = {};
+    uint64_t pin_bytes = 0;
+    void* wbuf = nullptr;
+    uint64_t wbytes = 0;
+};
+inline void host_pipe_destroy(HostPipe* hp) {
+    if (!hp) return;
+    for (int i = 0; i < HostPipe::NB; ++i) {
+        if (hp->dbuf[i]) rt::dfree(hp->dbuf[i]);
+        if (hp->pin_in[i]) rt::host_free_pinned(hp->pin_in[i]);
+        if (hp->pin_out[i]) rt::host_free_pinned(hp->pin_out[i]);
+        if (hp->ev_in[i]) rt::event_destroy(hp->ev_in[i]);
+        if (hp->ev_k[i]) rt::event_destroy(hp->ev_k[i]);
+        if (hp->ev_out[i]) rt::event_destroy(hp->ev_out[i]);
+    }
+    if (hp->wbuf) rt::dfree(hp->wbuf);
+    if (hp->s_in) rt::stream_destroy(hp->s_in);
+    if (hp->s_k) rt::stream_destroy(hp->s_k);
+    if (hp->s_out) rt::stream_destroy(hp->s_out);
+    delete hp;
+}
+
 }  // namespace b2
 
 struct b200fft_plan {
@@ -177,12 +209,17 @@ struct b200fft_plan {
         std::lock_guard<std::mutex> g(aux_mutex);
         aux_streams.push_back(s);
     }
+    // host-slice path: pipelines (streams, events, device ring, pinned staging ring, workspace) are created on first use and kept;
+    // one per concurrent caller
+    std::mutex pipe_mutex;
+    std::vector<b2::HostPipe*> pipes;
     std::function<bool(const b2::ExecCtx&)> exec;
     std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
     std::function<uint64_t(uint64_t)> launches = [](uint64_t) { return (uint64_t)0; };
     ~b200fft_plan() {
         for (void* p : tables) b2::rt::dfree(p);
         for (auto s : aux_streams) b2::rt::stream_destroy(s);
+        for (b2::HostPipe* hp : pipes) b2::host_pipe_destroy(hp);
     }
 };
 
@@ -266,7 +303,7 @@ static int overlap_streams(int auto_default = 2) {
 // B200FFT_FLOW=1: two-pass plans run as ONE launch of the dataflow kernel (kernels.h, run_flow) instead of one launch pair
 // per L2 chunk.  Opt-in: measured on B200 (profiles/r1t) it reaches 0.30-0.53 of the HBM roofline against 0.42-0.55 for
 // the chunked path -- the per-tile dependency/ticket/fence work costs more than the launch ramps and tails it removes.
-// B200FFT_FLOW_LOOKAHEAD = tickets pass A runs ahead of pass B (default 500), B200FFT_FLOW_W forces the ring slots.
+// B200FFT_FLOW_LOOKAHEAD = tickets pass A runs ahead of pass B (default 700), B200FFT_FLOW_W forces the ring slots.
 static bool use_flow() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_FLOW");
@@ -1507,6 +1544,10 @@ struct Builder {
             pl.desc = "Identity{" + std::to_string(n) + "}";
             return B200FFT_OK;
         }
+        // lengths this build cannot plan are rejected BEFORE any factoring / primality work (a prime near 2^62 would otherwise
+        // spin in trial division, and 2 n - 1 wraps above 2^63)
+        if (!hm::is_pow2(n) && n > (1ull << 23))
+            return fail(B200FFT_ERR_UNSUPPORTED, "non-power-of-two lengths above 2^23 are not planned by this build");
         bool ok = false;
         if (hm::is_pow2(n)) {
             if (n <= DirectMax<T>::v)
@@ -1584,7 +1625,8 @@ static int exec_device_impl(const b200fft_plan* pl, const void* d_in, void* d_ou
                             void* ws, uint64_t ws_bytes, bool ws_given, int max_streams = 0) {
     if (!pl || (!d_in && batch && pl->len) || (!d_out && batch && pl->len)) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
     if (pl->len == 0 || batch == 0) return B200FFT_OK;  // src/fft_helper.rs:16-18
-    if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    rt::DeviceGuard guard(pl->device);  // (restores the caller's current device on every exit path)
+    if (!guard.ok) return fail(B200FFT_ERR_CUDA, rt::last_error());
     const uint64_t need = pl->work_bytes(batch);
     void* work = ws;
     bool own = false;
@@ -1664,72 +1706,240 @@ static int exec_host_impl_2stream(const b200fft_plan* pl, const void* in, void* 
     return rc;
 }
 
-// Host-slice path (default; B200FFT_HOST_PIPE=2 selects the two-stream version above): a three-stage pipeline
-// over a ring of four device buffers -- one stream only copies in, one only computes, one only copies out,
-// ordered per chunk by events -- so both PCIe directions and the SMs are busy at once.  Measured on the round-1
-// box: 47.5 GB/s per direction for one-pass plans = the link's concurrent H2D+D2H limit (47.3 GB/s with plain
-// cudaMemcpyAsync), against 41-44 GB/s for the two-stream version.  Multi-pass plans run their chunks on the
-// single compute stream here (max_streams = 1): their internal two-stream overlap halved the copy rate.
-static int exec_host_impl(const b200fft_plan* pl, const void* in, void* out, uint64_t n_complex) {
+// ---- copy pool: a pageable caller's slices are copied to / from the pinned staging ring by several threads ------------------
+// (one thread moves ~10 GB/s; the link wants ~50 GB/s in each direction at once)
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool p;
+        return p;
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t MIN_PART = 4u << 20;
+        if (bytes < 2 * MIN_PART || workers_.empty()) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        std::unique_lock<std::mutex> job_lock(job_mutex_);  // one job at a time
+        const size_t parts = std::min<size_t>(workers_.size() + 1, (bytes + MIN_PART - 1) / MIN_PART);
+        const size_t per = ((bytes + parts - 1) / parts + 63) / 64 * 64;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = (char*)dst;
+            src_ = (const char*)src;
+            bytes_ = bytes;
+            per_ = per;
+            next_ = 1;  // part 0 is the caller's
+            parts_ = parts;
+            done_ = 0;
+            ++gen_;
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return done_ == parts_ - 1; });
+        parts_ = 0;
+    }
+
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char* e = std::getenv("B200FFT_COPY_THREADS");
+        unsigned n = e ? (unsigned)std::atoi(e) : std::min(12u, hw > 2 ? hw / 2 : 1u);
+        for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run() {
+        uint64_t seen = 0;
+        for (;;) {
+            size_t part;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && next_ < parts_) ; });
+                if (stop_) return;
+                part = next_++;
+                if (next_ >= parts_) seen = gen_;
+            }
+            const size_t off = part * per_;
+            if (off < bytes_) std::memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+            {
+                std::lock_guard<std::mutex> g(m_);
+                ++done_;
+            }
+            cv_done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, job_mutex_;
+    std::condition_variable cv_, cv_done_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0, next_ = 0, parts_ = 0, done_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+// Host-slice path (default; B200FFT_HOST_PIPE=2 selects the two-stream version above): a three-stage pipeline over a ring of four
+// device buffers -- one stream only copies in, one only computes, one only copies out, ordered per chunk by events -- so both PCIe
+// directions and the SMs are busy at once.  The pipeline's resources (streams, events, device ring, workspace, pinned staging ring)
+// belong to the plan: created on first use, reused by every later call (a batch-1 `process()` pays no allocation).  A caller's
+// pageable memory (what a Rust Vec is) cannot be the source of an asynchronous copy, so it is staged: copy-pool threads move slice c
+// into pinned slot c mod 4 while the device works on the slices before it, and finished slices back out; pinned / registered
+// buffers are used in place.  B200FFT_HOST_STAGE=0/1 forces the choice.
+static int exec_host_impl(const b200fft_plan* pl_c, const void* in, void* out, uint64_t n_complex) {
     static const bool three_stage = [] {
         const char* e = std::getenv("B200FFT_HOST_PIPE");
         return !(e && std::atoi(e) == 2);
     }();
-    if (!three_stage) return exec_host_impl_2stream(pl, in, out, n_complex);
-    if (!pl) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
-    if (pl->len == 0 || n_complex == 0) return B200FFT_OK;
+    if (!three_stage) return exec_host_impl_2stream(pl_c, in, out, n_complex);
+    if (!pl_c) return fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    if (pl_c->len == 0 || n_complex == 0) return B200FFT_OK;
     if (!in || !out) return fail(B200FFT_ERR_INVALID_ARG, "null buffer");
-    if (!rt::set_device(pl->device)) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    b200fft_plan* pl = const_cast<b200fft_plan*>(pl_c);  // (the pipeline pool is the plan's only mutable state, under its mutex)
+    rt::DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(B200FFT_ERR_CUDA, rt::last_error());
     const uint64_t esz = pl->precision == B200FFT_F32 ? 8 : 16;
     const uint64_t batch = n_complex / pl->len;
     const uint64_t tbytes = pl->len * esz;
     uint64_t chunk = std::max<uint64_t>(1, host_chunk_bytes_cfg() / tbytes);
     if (chunk > batch) chunk = batch;
     const uint64_t nchunks = (batch + chunk - 1) / chunk;
-    const int NB = (int)std::min<uint64_t>(4, nchunks);
-    void* dbuf[4] = {nullptr, nullptr, nullptr, nullptr};
-    rt::event_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_k[4] = {nullptr, nullptr, nullptr, nullptr},
-                ev_out[4] = {nullptr, nullptr, nullptr, nullptr};
-    rt::stream_t s_in = rt::stream_create(), s_k = rt::stream_create(), s_out = rt::stream_create();
-    const uint64_t wbytes = pl->work_bytes(chunk);
-    void* wbuf = wbytes ? rt::dmalloc(wbytes) : nullptr;
-    int rc = B200FFT_OK;
-    if (!s_in || !s_k || !s_out || (wbytes && !wbuf)) rc = fail(B200FFT_ERR_CUDA, "staging allocation failed: " + rt::last_error());
-    for (int i = 0; i < NB && rc == B200FFT_OK; ++i) {
-        dbuf[i] = rt::dmalloc(chunk * tbytes);
-        ev_in[i] = rt::event_create();
-        ev_k[i] = rt::event_create();
-        ev_out[i] = rt::event_create();
-        if (!dbuf[i] || !ev_in[i] || !ev_k[i] || !ev_out[i]) rc = fail(B200FFT_ERR_CUDA, "staging allocation failed: " + rt::last_error());
+    static const int force_stage = [] {
+        const char* e = std::getenv("B200FFT_HOST_STAGE");
+        return e ? std::atoi(e) : -1;
+    }();
+    const bool stage = force_stage >= 0 ? force_stage != 0 : !(rt::host_is_pinned(in) && rt::host_is_pinned(out));
+    constexpr int NB = HostPipe::NB;
+
+    HostPipe* hp = nullptr;
+    {
+        std::lock_guard<std::mutex> g(pl->pipe_mutex);
+        if (!pl->pipes.empty()) {
+            hp = pl->pipes.back();
+            pl->pipes.pop_back();
+        }
     }
-    uint64_t idx = 0;
+    if (!hp) hp = new HostPipe();
+    int rc = B200FFT_OK;
+    auto cuda_fail = [&](const char* what) { return fail(B200FFT_ERR_CUDA, std::string(what) + ": " + rt::last_error()); };
+    // (re)size the resources
+    const uint64_t need_buf = chunk * tbytes, need_w = pl->work_bytes(chunk);
+    const int slots = (int)std::min<uint64_t>(NB, nchunks);
+    if (!hp->s_in) {
+        hp->s_in = rt::stream_create();
+        hp->s_k = rt::stream_create();
+        hp->s_out = rt::stream_create();
+        for (int i = 0; i < NB; ++i) {
+            hp->ev_in[i] = rt::event_create();
+            hp->ev_k[i] = rt::event_create();
+            hp->ev_out[i] = rt::event_create();
+        }
+        if (!hp->s_in || !hp->s_k || !hp->s_out || !hp->ev_out[NB - 1]) rc = cuda_fail("pipeline creation failed");
+    }
+    if (rc == B200FFT_OK && (hp->dbuf_bytes < need_buf || !hp->dbuf[slots - 1])) {
+        const uint64_t sz = std::max(hp->dbuf_bytes, need_buf);
+        for (int i = 0; i < NB; ++i) {
+            if (hp->dbuf[i] && hp->dbuf_bytes < sz) {
+                rt::dfree(hp->dbuf[i]);
+                hp->dbuf[i] = nullptr;
+            }
+            if (i < slots && !hp->dbuf[i]) {
+                hp->dbuf[i] = rt::dmalloc(sz);
+                if (!hp->dbuf[i]) {
+                    rc = cuda_fail("device ring allocation failed");
+                    break;
+                }
+            }
+        }
+        hp->dbuf_bytes = sz;
+    }
+    if (rc == B200FFT_OK && stage && (hp->pin_bytes < need_buf || !hp->pin_in[slots - 1])) {
+        const uint64_t sz = std::max(hp->pin_bytes, need_buf);
+        for (int i = 0; i < NB; ++i) {
+            if (hp->pin_in[i] && hp->pin_bytes < sz) {
+                rt::host_free_pinned(hp->pin_in[i]);
+                rt::host_free_pinned(hp->pin_out[i]);
+                hp->pin_in[i] = hp->pin_out[i] = nullptr;
+            }
+            if (i < slots && !hp->pin_in[i]) {
+                hp->pin_in[i] = rt::host_alloc_pinned(sz);
+                hp->pin_out[i] = rt::host_alloc_pinned(sz);
+                if (!hp->pin_in[i] || !hp->pin_out[i]) {
+                    rc = cuda_fail("pinned staging allocation failed");
+                    break;
+                }
+            }
+        }
+        hp->pin_bytes = sz;
+    }
+    if (rc == B200FFT_OK && need_w > hp->wbytes) {
+        if (hp->wbuf) rt::dfree(hp->wbuf);
+        hp->wbuf = rt::dmalloc(need_w);
+        hp->wbytes = hp->wbuf ? need_w : 0;
+        if (!hp->wbuf) rc = cuda_fail("workspace allocation failed");
+    }
+
+    CopyPool& pool = CopyPool::get();
+    auto drain = [&](uint64_t idx) {  // staged: slice idx has been copied out to its pinned slot -> the caller's memory
+        const int b = (int)(idx % (uint64_t)NB);
+        const uint64_t b0 = idx * chunk, nb = std::min(chunk, batch - b0);
+        if (!rt::event_sync(hp->ev_out[b])) return false;
+        pool.copy((char*)out + b0 * tbytes, hp->pin_out[b], nb * tbytes);
+        return true;
+    };
+    uint64_t idx = 0, drained = 0;
     for (uint64_t b0 = 0; b0 < batch && rc == B200FFT_OK; b0 += chunk, ++idx) {
         const int b = (int)(idx % (uint64_t)NB);
         const uint64_t nb = std::min(chunk, batch - b0);
         const char* src = (const char*)in + b0 * tbytes;
         char* dst = (char*)out + b0 * tbytes;
         bool ok = true;
-        if (idx >= (uint64_t)NB) ok = rt::stream_wait(s_in, ev_out[b]);  // ring slot drained
-        ok = ok && rt::h2d_async(dbuf[b], src, nb * tbytes, s_in) && rt::event_record(ev_in[b], s_in) && rt::stream_wait(s_k, ev_in[b]);
-        if (!ok) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
-        rc = exec_device_impl(pl, dbuf[b], dbuf[b], nb, s_k, wbuf, wbytes, wbytes != 0, 1);
+        if (stage) {
+            if (idx >= (uint64_t)NB) {  // the slot's previous slice must be out of the staging buffers before they are refilled
+                ok = drain(drained);
+                ++drained;
+            }
+            if (ok) pool.copy(hp->pin_in[b], src, nb * tbytes);
+            src = (const char*)hp->pin_in[b];
+            dst = (char*)hp->pin_out[b];
+        } else if (idx >= (uint64_t)NB) {
+            ok = rt::stream_wait(hp->s_in, hp->ev_out[b]);  // ring slot drained
+        }
+        ok = ok && rt::h2d_async(hp->dbuf[b], src, nb * tbytes, hp->s_in) && rt::event_record(hp->ev_in[b], hp->s_in) &&
+             rt::stream_wait(hp->s_k, hp->ev_in[b]);
+        if (!ok) {
+            rc = cuda_fail("host pipeline (copy in)");
+            break;
+        }
+        rc = exec_device_impl(pl, hp->dbuf[b], hp->dbuf[b], nb, hp->s_k, hp->wbuf, hp->wbytes, hp->wbytes != 0, 1);
         if (rc != B200FFT_OK) break;
-        ok = rt::event_record(ev_k[b], s_k) && rt::stream_wait(s_out, ev_k[b]) && rt::d2h_async(dst, dbuf[b], nb * tbytes, s_out) &&
-             rt::event_record(ev_out[b], s_out);
-        if (!ok) { rc = fail(B200FFT_ERR_CUDA, rt::last_error()); break; }
+        ok = rt::event_record(hp->ev_k[b], hp->s_k) && rt::stream_wait(hp->s_out, hp->ev_k[b]) && rt::d2h_async(dst, hp->dbuf[b], nb * tbytes, hp->s_out) &&
+             rt::event_record(hp->ev_out[b], hp->s_out);
+        if (!ok) {
+            rc = cuda_fail("host pipeline (copy out)");
+            break;
+        }
     }
-    rt::stream_t all[3] = {s_in, s_k, s_out};
-    for (rt::stream_t s : all)
-        if (s && !rt::stream_sync(s) && rc == B200FFT_OK) rc = fail(B200FFT_ERR_CUDA, rt::last_error());
-    for (int i = 0; i < 4; ++i) {
-        if (dbuf[i]) rt::dfree(dbuf[i]);
-        if (ev_in[i]) rt::event_destroy(ev_in[i]);
-        if (ev_k[i]) rt::event_destroy(ev_k[i]);
-        if (ev_out[i]) rt::event_destroy(ev_out[i]);
+    if (stage && rc == B200FFT_OK)
+        for (; drained < idx; ++drained)
+            if (!drain(drained)) {
+                rc = cuda_fail("host pipeline (drain)");
+                break;
+            }
+    rt::stream_t all[3] = {hp->s_in, hp->s_k, hp->s_out};
+    for (rt::stream_t st : all)
+        if (st && !rt::stream_sync(st) && rc == B200FFT_OK) rc = cuda_fail("host pipeline (sync)");
+    {
+        std::lock_guard<std::mutex> g(pl->pipe_mutex);
+        pl->pipes.push_back(hp);
     }
-    if (wbuf) rt::dfree(wbuf);
-    for (rt::stream_t s : all)
-        if (s) rt::stream_destroy(s);
     return rc;
 }
 

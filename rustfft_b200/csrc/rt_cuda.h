@@ -16,7 +16,7 @@ namespace rt {
 
 typedef cudaStream_t stream_t;
 
-static thread_local std::string g_err;
+inline thread_local std::string g_err;  // (inline: ONE instance for all translation units of the library)
 static bool check(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -79,6 +79,36 @@ static event_t event_create() {
 static void event_destroy(event_t e) { cudaEventDestroy(e); }
 static bool event_record(event_t e, stream_t s) { return check(cudaEventRecord(e, s), "cudaEventRecord"); }
 static bool stream_wait(stream_t s, event_t e) { return check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
+static bool event_sync(event_t e) { return check(cudaEventSynchronize(e), "cudaEventSynchronize"); }
+// page-locked host memory for the staging rings of the host-slice path
+static void* host_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (!check(cudaHostAlloc(&p, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+static void host_free_pinned(void* p) { cudaFreeHost(p); }
+// true when the device can DMA straight from / to this host pointer (pinned or registered); pageable memory is staged
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+// RAII: the library never leaves the calling thread on another device than it found it on
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = check(cudaSetDevice(dev), "cudaSetDevice");
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // ---- L2 persistence for the L2-resident intermediate of two-pass plans ---------------------------------------
 // B200FFT_L2_PERSIST_MB = N (N > 0): reserve N MiB of L2 for persisting lines (cudaLimitPersistingL2CacheSize, a

@@ -47,9 +47,11 @@ class ShardedFft:
         """Root holds batch*n elements; every rank gets its contiguous shard."""
         lo, hi = self.my_range(batch)
         if self.world == 1:
-            return full[lo * self.n: hi * self.n]
+            return full[lo * self.n: hi * self.n].clone()  # a copy, as for world > 1: process_local never touches `full`
         if self.rank == root:
             device, dtype = full.device, full.dtype
+        elif device is None or dtype is None:
+            raise ValueError("scatter(): ranks other than root must pass the shard's device and dtype")
         mine = torch.empty((hi - lo) * self.n, dtype=dtype, device=device)
         ops = []
         if self.rank == root:

@@ -40,6 +40,14 @@ static event_t event_create() { return (event_t)1; }
 static void event_destroy(event_t) {}
 static bool event_record(event_t, stream_t) { return true; }
 static bool stream_wait(stream_t, event_t) { return true; }
+static bool event_sync(event_t) { return true; }
+static void* host_alloc_pinned(size_t n) { return std::malloc(n ? n : 1); }
+static void host_free_pinned(void* p) { std::free(p); }
+static bool host_is_pinned(const void*) { return false; }  // exercise the staged path on the CPU
+struct DeviceGuard {
+    bool ok = true;
+    explicit DeviceGuard(int) {}
+};
 }  // namespace rt
 }  // namespace b2
 
