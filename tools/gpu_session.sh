@@ -1,11 +1,18 @@
 #!/bin/bash
-OUT=gpurun_out/s11
+OUT=gpurun_out/s12
 mkdir -p $OUT
 export PYTHONPATH=$PWD:$PWD/tests
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "config2_power or up_to_2_24 or ragged or device_path" > $OUT/pytest_quick.log 2>&1
-echo "pytest quick rc=$?" >> $OUT/pytest_quick.log
-tail -n 3 $OUT/pytest_quick.log
-for v in "" "B200FFT_FUSED_TW2=0"; do
-  env $v timeout 200 python tools/ab_two_pass.py 15,16,17,18,19,20 >> $OUT/ab.log 2>&1
-done
-grep SUMMARY $OUT/ab.log
+nproc > $OUT/host.txt; free -g >> $OUT/host.txt; lscpu | head -20 >> $OUT/host.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "host or device_path or threads or error_behaviour" > $OUT/pytest_host.log 2>&1
+echo "pytest rc=$?" >> $OUT/pytest_host.log
+tail -n 3 $OUT/pytest_host.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
+tail -c 1500 $OUT/bench_ref.json
+timeout 900 python bench.py --no-extras > $OUT/bench.json 2> $OUT/bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/s12/bench.json'))
+print("value",d["value"],"frac",d["roofline"]["frac"])
+print("e2e",json.dumps(d["e2e"]))
+print("cpu",json.dumps({k:v for k,v in d["cpu_baseline"].items() if k!="per_size"}))
+PY
