@@ -594,6 +594,128 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "gflops": round(5 * 65536 * 16 * 65536 / (ms * 1e-3) / 1e9, 1),
                        "frac_per_gpu": round(16.0 * 65536 * per_rank / (ms * 1e-3) / 1e9 / hbm, 4)})
 
+        # f64 forward sweep (the same device path; 2^14 and up are two-pass plans of chunked launch pairs in f64)
+        try:
+            src64 = src.view(torch.float32).view(torch.complex128)
+            dst64 = dst.view(torch.float32).view(torch.complex128)
+            rows64, tot_b, tot_ms = [], 0.0, 0.0
+            for lg in range(10, 19):
+                n = 1 << lg
+                f = p64.plan_fft_forward(n)
+                ws64 = torch.empty(max(f.workspace_bytes(BATCH), 16), dtype=torch.uint8, device=dev)
+                off = ((lg - 10) * (1 << 27)) % max(1, src64.numel() - BATCH * n)  # a different region per size
+
+                def c64():
+                    f.process_device(src64[off: off + BATCH * n], out=dst64[off: off + BATCH * n], workspace=ws64)
+
+                ms = timed(c64, 3)
+                rows64.append({"log2n": lg, "plan": f.describe(), "ms": round(ms, 4), "frac": round(32.0 * n * BATCH / (ms * 1e-3) / 1e9 / hbm, 4)})
+                tot_b += 32.0 * n * BATCH
+                tot_ms += ms
+                del ws64
+            extras.append({"config": "f64 forward N=2^10..2^18 batch=4096 (informational)", "ms": round(tot_ms, 3),
+                           "frac": round(tot_b / (tot_ms * 1e-3) / 1e9 / hbm, 4), "per_size": rows64})
+        except Exception as e:  # pragma: no cover
+            extras.append({"config": "f64 sweep (informational)", "error": f"{type(e).__name__}: {e}"[:200]})
+
+        # stated tolerance, as numbers: error of this library's output on the reference's test distribution (U[0,10), tests/accuracy.rs:86)
+        # against an f64 / longdouble-free numpy truth, per BASELINE config -- relative L2, and the largest element error in units of
+        # eps x output RMS ("ulp_rms"); `bound` is what the parity tests enforce (4 eps log2 N, tests/util.py)
+        if rank == 0:
+            try:
+                acc = []
+
+                def acc_row(name, pl, n, nb, dt, roundtrip=False):
+                    rng = np.random.default_rng(n)
+                    x = ((rng.random(n * nb) + 1j * rng.random(n * nb)) * 10).astype(dt)
+                    d = torch.from_numpy(x).to(dev)
+                    f = pl.plan_fft_forward(n)
+                    f.process_device(d)
+                    eps = 5.96e-8 if dt == np.complex64 else 1.11e-16
+                    if roundtrip:
+                        pl.plan_fft_inverse(n).process_device(d)
+                        got = d.cpu().numpy().astype(np.complex128) / n
+                        ref = x.astype(np.complex128)
+                    else:
+                        got = d.cpu().numpy().astype(np.complex128)
+                        ref = np.fft.fft(x.astype(np.complex128).reshape(nb, n), axis=1).ravel()
+                    err = got - ref
+                    rms = float(np.sqrt(np.mean(np.abs(ref) ** 2)))
+                    acc.append({"config": name, "plan": f.describe(), "rel_l2": float(f"{np.linalg.norm(err) / np.linalg.norm(ref):.3e}"),
+                                "max_err_ulp_rms": round(float(np.max(np.abs(err)) / (eps * rms)), 2),
+                                "bound_rel_l2": float(f"{4 * eps * max(1.0, np.log2(n)) * (2 if roundtrip else 1):.3e}")})
+
+                for lg in (10, 15, 20):
+                    acc_row(f"f32 forward N=2^{lg}", planner, 1 << lg, 4 if lg < 20 else 1, np.complex64)
+                acc_row("f64 forward+inverse N=1234 (x/N vs input)", p64, 1234, 8, np.complex128, roundtrip=True)
+                acc_row("f64 forward N=1234", p64, 1234, 8, np.complex128)
+                acc_row("f32 prime N=65537", planner, 65537, 2, np.complex64)
+                acc_row("f32 N=2^16", planner, 1 << 16, 4, np.complex64)
+                extras.append({"config": "accuracy (stated tolerance as measured numbers)", "rows": acc})
+            except Exception as e:  # pragma: no cover
+                extras.append({"config": "accuracy", "error": f"{type(e).__name__}: {e}"[:200]})
+
+        # config 5 as north_star states it (only with > 1 rank): the whole batch starts on GPU 0, NCCL point-to-point scatter of
+        # contiguous batch shards over NVLink -> every rank transforms its shard -> gather back to GPU 0; the three stages
+        # are timed separately (device events, max over ranks) and sampled transforms are checked against the CPU oracle
+        if dist:
+            try:
+                from rustfft_b200.sharded import ShardedFft
+
+                sh = ShardedFft(planner, 1 << 16)
+                B5 = 65536
+                full = src[: B5 << 16] if rank == 0 else None
+                lo5, hi5 = sh.my_range(B5)
+
+                def ev_ms(fn):
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    return r, tt.item()
+
+                stage_ms = {"scatter": [], "fft": [], "gather": []}
+                for it in range(3):  # first pass = warm-up (NCCL channel setup), the other two are averaged
+                    shard, t_s = ev_ms(lambda: sh.scatter(full, B5, root=0, device=dev, dtype=torch.complex64))
+                    _, t_f = ev_ms(lambda: sh.process_local(shard))
+                    _, t_g = ev_ms(lambda: sh.gather(shard, B5, root=0, out=dst if rank == 0 else None))
+                    if it:
+                        stage_ms["scatter"].append(t_s)
+                        stage_ms["fft"].append(t_f)
+                        stage_ms["gather"].append(t_g)
+                    if it < 2:
+                        del shard
+                ms5 = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+                moved = (B5 - (hi5 - lo5 if rank == 0 else B5 // world)) * 65536 * 8.0  # bytes leaving / entering GPU 0
+                row = {"config": f"f32 N=2^16 batch=65536: NCCL scatter from GPU 0 -> FFT on {world} GPUs -> gather to GPU 0",
+                       "plan": sh.fft.describe(), "ms_scatter": round(ms5["scatter"], 3), "ms_fft": round(ms5["fft"], 3),
+                       "ms_gather": round(ms5["gather"], 3),
+                       "root_egress_gbs": round(moved / (ms5["scatter"] * 1e-3) / 1e9, 1),
+                       "root_ingress_gbs": round(moved / (ms5["gather"] * 1e-3) / 1e9, 1),
+                       "gflops_fft_only": round(5 * 65536 * 16 * B5 / (ms5["fft"] * 1e-3) / 1e9, 1),
+                       "gflops_with_scatter_gather": round(5 * 65536 * 16 * B5 / ((ms5["scatter"] + ms5["fft"] + ms5["gather"]) * 1e-3) / 1e9, 1),
+                       "limiter": "GPU 0's NVLink egress (scatter) and ingress (gather): (world-1)/world of 32 GiB each way through one GPU's links"}
+                if rank == 0:
+                    import oracle
+
+                    oracle.build()
+                    worst = 0.0
+                    for b in (0, B5 // world, B5 // 2 + 3, B5 - 1):  # first shard, first transform of rank 1's, a middle one, the last
+                        xb = src[b << 16:(b + 1) << 16].cpu().numpy()
+                        yb = dst[b << 16:(b + 1) << 16].cpu().numpy()
+                        want = oracle.fft(xb, 1 << 16)
+                        worst = max(worst, float(np.linalg.norm(yb - want) / np.linalg.norm(want)))
+                    row["checked_vs_oracle"] = {"transforms": 4, "max_rel_l2": float(f"{worst:.3e}"), "bound": 4 * 5.96e-8 * 16,
+                                                "ok": bool(worst <= 2 * 4 * 5.96e-8 * 16)}
+                extras.append(row)
+                del shard
+            except Exception as e:  # pragma: no cover
+                extras.append({"config": "config 5 with NCCL scatter/gather", "error": f"{type(e).__name__}: {e}"[:300]})
+
         # informational: composite lengths of small primes through the two-pass SmoothFourStep plans (not a BASELINE
         # config; guarded so that a problem here can never cost the bench line)
         try:

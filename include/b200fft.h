@@ -10,6 +10,8 @@
  *     (src/avx/avx_planner.rs:121-164, probed in             (0 devices => the Rust shim's new() returns
  *      FftPlanner::new, src/plan.rs:72-94)                    Err(()) and the next backend is tried)
  *   FftPlanner::plan_fft(len, direction) -> Arc<dyn Fft<T>>  b200fft_plan_create() / b200fft_plan_destroy()
+ *   FftPlannerScalar::design_fft_for_len -> Recipe           b200fft_plan_create_from_recipe()  (the host keeps
+ *     (src/plan.rs:134-226,412-425) + build_fft (:315-410)     planning; the library builds what the recipe says)
  *     (src/plan.rs:101-126; instances cached per             (the shim keeps RustFFT's FftCache,
  *      (len, direction), src/fft_cache.rs:5-38)               src/fft_cache.rs, above this call)
  *   Length::len / Direction::fft_direction                   b200fft_plan_len() / b200fft_plan_direction()
@@ -68,6 +70,37 @@ int b200fft_device_count(int* n);
  * (angles evaluated in extended precision, rounded once -- src/twiddles.rs:6-23 contract) and uploads them. */
 int b200fft_plan_create(b200fft_plan** out, uint64_t len, int direction, int precision, int device);
 int b200fft_plan_destroy(b200fft_plan* plan);
+
+/* Planning owned by the caller (the Rust host code of a `src/cuda/` backend keeps src/plan.rs's design_fft_* and hands the
+ * decomposition over as data): a flattened recipe tree, node 0 = the root, in the vocabulary of the reference's Recipe enum
+ * (src/plan.rs:134-226).  The library maps each node onto its kernels or returns B200FFT_ERR_UNSUPPORTED; tables are always
+ * recomputed here in extended precision (src/twiddles.rs:6-23 contract), so no host twiddles cross the boundary.
+ *   kind          reference Recipe                      a, b, child
+ *   AUTO          --                                    this library's own choice for `len`
+ *   POW2          Radix4 / Butterfly2..32               --  (len = 2^k: one CTA pass up to 2^14, two passes up to 2^24)
+ *   SMOOTH        RadixN / Butterfly3..31               --  (prime factors <= 31, one CTA pass)
+ *   MIXED_RADIX   MixedRadix / MixedRadixSmall          len = a * b, two passes (a x b)
+ *   GOOD_THOMAS   GoodThomasAlgorithm(+Small)           len = a * b, gcd(a, b) = 1, two passes without twiddles
+ *   RADER         RadersAlgorithm                       len = a * p (a = 0 or 1: len = p prime; a in 2..8: MixedRadix{a x Rader(p)}
+ *                                                       fused); child = node of the inner FFT of length p - 1 (0 = AUTO)
+ *   BLUESTEIN     BluesteinsAlgorithm                   child = node of the inner FFT, length M >= 2 len - 1 (0 = AUTO) */
+enum {
+    B200FFT_RECIPE_AUTO = 0,
+    B200FFT_RECIPE_POW2 = 1,
+    B200FFT_RECIPE_SMOOTH = 2,
+    B200FFT_RECIPE_MIXED_RADIX = 3,
+    B200FFT_RECIPE_GOOD_THOMAS = 4,
+    B200FFT_RECIPE_RADER = 5,
+    B200FFT_RECIPE_BLUESTEIN = 6
+};
+typedef struct b200fft_recipe_node {
+    uint32_t kind;  /* B200FFT_RECIPE_* */
+    uint32_t child; /* index of the inner-FFT node (RADER / BLUESTEIN); 0 = let the library choose */
+    uint64_t len;   /* length of this node's transform */
+    uint64_t a, b;  /* MIXED_RADIX / GOOD_THOMAS: the split; RADER: a = outer radix */
+} b200fft_recipe_node;
+int b200fft_plan_create_from_recipe(b200fft_plan** out, const b200fft_recipe_node* nodes, uint32_t n_nodes, int direction,
+                                    int precision, int device);
 
 uint64_t b200fft_plan_len(const b200fft_plan* plan);
 int b200fft_plan_direction(const b200fft_plan* plan);

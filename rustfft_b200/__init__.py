@@ -26,7 +26,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "default_library", "shard_range"]
+__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "Recipe", "default_library", "shard_range"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200FFT_LIB: load another build of the same C ABI (A/B measurements of kernel variants; tools/ab_two_pass.py)
@@ -51,11 +51,60 @@ class FftDirection(enum.IntEnum):
         return FftDirection.Inverse if self == FftDirection.Forward else FftDirection.Forward
 
 
+class _RecipeNode(ctypes.Structure):  # b200fft_recipe_node (include/b200fft.h)
+    _fields_ = [("kind", ctypes.c_uint32), ("child", ctypes.c_uint32), ("len", ctypes.c_uint64), ("a", ctypes.c_uint64), ("b", ctypes.c_uint64)]
+
+
+class Recipe:
+    """A decomposition chosen by the host (the reference's Recipe enum, src/plan.rs:134-226) handed to the library as data.
+
+    Built with the class methods; `inner` is the Recipe of the inner FFT of a Rader / Bluestein node."""
+
+    AUTO, POW2, SMOOTH, MIXED_RADIX, GOOD_THOMAS, RADER, BLUESTEIN = range(7)
+
+    def __init__(self, kind: int, len: int, a: int = 0, b: int = 0, inner: Optional["Recipe"] = None):
+        self.kind, self.len, self.a, self.b, self.inner = kind, int(len), int(a), int(b), inner
+
+    @classmethod
+    def pow2(cls, n):
+        return cls(cls.POW2, n)
+
+    @classmethod
+    def smooth(cls, n):
+        return cls(cls.SMOOTH, n)
+
+    @classmethod
+    def mixed_radix(cls, a, b):
+        return cls(cls.MIXED_RADIX, a * b, a, b)
+
+    @classmethod
+    def good_thomas(cls, a, b):
+        return cls(cls.GOOD_THOMAS, a * b, a, b)
+
+    @classmethod
+    def rader(cls, n, outer_radix=1, inner: Optional["Recipe"] = None):
+        return cls(cls.RADER, n, outer_radix, 0, inner)
+
+    @classmethod
+    def bluestein(cls, n, inner: Optional["Recipe"] = None):
+        return cls(cls.BLUESTEIN, n, 0, 0, inner)
+
+    def flatten(self):
+        nodes, r = [], self
+        while r is not None:
+            nodes.append(r)
+            r = r.inner
+        arr = (_RecipeNode * len(nodes))()
+        for i, r in enumerate(nodes):
+            arr[i] = _RecipeNode(r.kind, i + 1 if r.inner is not None else 0, r.len, r.a, r.b)
+        return arr
+
+
 class Library:
     """A loaded C-ABI library (include/b200fft.h)."""
 
     SYMBOLS = [
-        "b200fft_device_count", "b200fft_plan_create", "b200fft_plan_destroy", "b200fft_plan_len",
+        "b200fft_device_count", "b200fft_plan_create", "b200fft_plan_create_from_recipe", "b200fft_plan_destroy", "b200fft_plan_len",
         "b200fft_plan_direction", "b200fft_plan_precision", "b200fft_plan_scratch_len", "b200fft_plan_describe",
         "b200fft_plan_launches", "b200fft_exec_host_inplace", "b200fft_exec_host_outofplace", "b200fft_exec_device",
         "b200fft_workspace_bytes", "b200fft_exec_device_ws", "b200fft_last_error", "b200fft_version",
@@ -70,6 +119,7 @@ class Library:
         c, u64, i32, vp = self.c, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p
         c.b200fft_device_count.argtypes = [ctypes.POINTER(i32)]
         c.b200fft_plan_create.argtypes = [ctypes.POINTER(vp), u64, i32, i32, i32]
+        c.b200fft_plan_create_from_recipe.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_RecipeNode), ctypes.c_uint32, i32, i32, i32]
         c.b200fft_plan_destroy.argtypes = [vp]
         c.b200fft_plan_len.argtypes = [vp]
         c.b200fft_plan_len.restype = u64
@@ -122,10 +172,14 @@ class Fft:
 
     Immutable after construction and safe to call from many threads (examples/concurrency.rs)."""
 
-    def __init__(self, lib: Library, length: int, direction: FftDirection, precision: int, device: int):
+    def __init__(self, lib: Library, length: int, direction: FftDirection, precision: int, device: int, recipe: Optional[Recipe] = None):
         self._lib = lib
         self._h = ctypes.c_void_p()
-        lib.check(lib.c.b200fft_plan_create(ctypes.byref(self._h), length, int(direction), precision, device))
+        if recipe is not None:
+            nodes = recipe.flatten()
+            lib.check(lib.c.b200fft_plan_create_from_recipe(ctypes.byref(self._h), nodes, len(nodes), int(direction), precision, device))
+        else:
+            lib.check(lib.c.b200fft_plan_create(ctypes.byref(self._h), length, int(direction), precision, device))
         self._len = length
         self._direction = FftDirection(direction)
         self._precision = precision
@@ -291,6 +345,10 @@ class FftPlanner:
                 fft = Fft(self._lib, int(len), FftDirection(direction), self._precision, self.device)
                 self._cache[key] = fft
             return fft
+
+    def plan_fft_with_recipe(self, recipe: Recipe, direction: FftDirection) -> Fft:
+        """Planning owned by the caller: build exactly the decomposition `recipe` names (not cached)."""
+        return Fft(self._lib, recipe.len, FftDirection(direction), self._precision, self.device, recipe=recipe)
 
     def plan_fft_forward(self, len: int) -> Fft:
         return self.plan_fft(len, FftDirection.Forward)

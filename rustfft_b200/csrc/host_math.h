@@ -71,6 +71,42 @@ inline void fft_pow2_ld(std::vector<cld>& a) {
     }
 }
 
+// forward FFT of any length whose prime factors are small, long double: recursive decimation in time by the smallest
+// prime factor r of the length (r interleaved sub-transforms, then r-point DFTs across them).  Plan-time only: the
+// multipliers of Rader / Bluestein plans over smooth inner lengths.
+inline void fft_any_ld_rec(const cld* in, size_t stride, cld* out, size_t n, const std::vector<cld>& wn, size_t wstep) {
+    if (n == 1) {
+        out[0] = in[0];
+        return;
+    }
+    size_t r = 2;
+    while (n % r) ++r;
+    const size_t m = n / r;
+    for (size_t j = 0; j < r; ++j) fft_any_ld_rec(in + j * stride, stride * r, out + j * m, m, wn, wstep * r);
+    std::vector<cld> t(r);
+    for (size_t k = 0; k < m; ++k) {
+        for (size_t j = 0; j < r; ++j) t[j] = mul(out[j * m + k], wn[(j * k * wstep) % wn.size()]);
+        for (size_t q = 0; q < r; ++q) {
+            cld acc{0, 0};
+            for (size_t j = 0; j < r; ++j) {
+                const cld v = mul(t[j], wn[(j * q * m * wstep) % wn.size()]);
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            // (out[q m + k] for all q are read above before any is written: t[] holds them)
+            out[q * m + k] = acc;
+        }
+    }
+}
+inline void fft_any_ld(std::vector<cld>& a) {
+    const size_t n = a.size();
+    if (n < 2) return;
+    std::vector<cld> wn(n), out(n);
+    for (size_t k = 0; k < n; ++k) wn[k] = twiddle_ld(k, n);
+    fft_any_ld_rec(a.data(), 1, out.data(), n, wn, 1);
+    a.swap(out);
+}
+
 inline bool is_pow2(uint64_t n) { return n && !(n & (n - 1)); }
 inline uint32_t ilog2(uint64_t n) {
     uint32_t l = 0;
@@ -98,6 +134,38 @@ inline uint64_t powmod(uint64_t b, uint64_t e, uint64_t m) {
         e >>= 1;
     }
     return r;
+}
+inline uint64_t gcd(uint64_t a, uint64_t b) {
+    while (b) {
+        const uint64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+// a^-1 mod m (gcd(a, m) = 1, m > 1), extended Euclid
+inline uint64_t invmod(uint64_t a, uint64_t m) {
+    __int128 t = 0, nt = 1, r = (__int128)m, nr = (__int128)(a % m);
+    while (nr != 0) {
+        const __int128 q = r / nr;
+        __int128 x = t - q * nt;
+        t = nt;
+        nt = x;
+        x = r - q * nr;
+        r = nr;
+        nr = x;
+    }
+    if (t < 0) t += (__int128)m;
+    return (uint64_t)t;
+}
+inline uint64_t largest_prime_factor(uint64_t n) {
+    uint64_t best = 1;
+    for (uint64_t d = 2; d * d <= n; ++d)
+        while (n % d == 0) {
+            best = d;
+            n /= d;
+        }
+    return n > 1 ? n : best;
 }
 // smallest primitive root of prime p (same choice as src/math_utils.rs:3-20)
 inline uint64_t primitive_root(uint64_t p) {

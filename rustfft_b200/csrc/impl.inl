@@ -10,6 +10,7 @@
 //   prime factors <= 31, n <= 4096 -> Smooth     one CTA pass, run-time radix list (31..11/7/5/3/16/8/4/2)
 //   prime n, n-1 = 2^k            -> Rader       (fused single pass when n-1 <= 256, else over FourStep)
 //   anything else                 -> Bluestein   M = next_pow2(2n-1)  (fused single pass when M <= 4096)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -213,6 +214,7 @@ struct b200fft_plan {
     // one per concurrent caller
     std::mutex pipe_mutex;
     std::vector<b2::HostPipe*> pipes;
+    std::vector<b200fft_recipe_node> recipe;  // b200fft_plan_create_from_recipe: the caller's decomposition (empty = plan here)
     std::function<bool(const b2::ExecCtx&)> exec;
     std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
     std::function<uint64_t(uint64_t)> launches = [](uint64_t) { return (uint64_t)0; };
@@ -480,8 +482,15 @@ struct Builder {
         else
             return build_smooth_f64(pl, kind, a, b);
     }
+    // kind 0: Smooth; 1: SmoothFourStep{a x b}; 2: one-pass Rader, outer radix a, prime b; 3: one-pass Bluestein, inner M = a;
+    //      4: GoodThomas{a x b}; 5: Rader over SmoothFourStep{a x b}; 6: Bluestein over SmoothFourStep{a x b}
     static bool smooth_build_here(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
-        if (kind == 1) return make_smooth_four_step(pl, a, b);
+        if (kind == 1) return make_smooth_four_step(pl, a, b, 0);
+        if (kind == 4) return make_smooth_four_step(pl, a, b, 1);
+        if (kind == 2) return make_smooth_conv(pl, 0, a, b);
+        if (kind == 3) return make_smooth_conv(pl, 1, 1, a);
+        if (kind == 5) return make_smooth_big_conv(pl, a, b, true);
+        if (kind == 6) return make_smooth_big_conv(pl, a, b, false);
         std::vector<uint32_t> radices;
         return smooth_factor(pl.len, radices) && make_smooth(pl, radices);
     }
@@ -1338,32 +1347,23 @@ struct Builder {
         base.n_stages = (uint32_t)radices.size();
         return base.tw != nullptr;
     }
-    template <bool SW>
-    static bool make_smooth_four_step_t(b200fft_plan& pl, uint32_t N1, uint32_t N2) {
-        using KA = SmoothPassKernel<T, SW, 1>;
-        using KB = SmoothPassKernel<T, SW, 2>;
+    // geometry of the two passes of a smooth N1 x N2 split (shared by SmoothFourStep, GoodThomas and the large convolution plans)
+    template <class KA, class KB>
+    static bool smooth_pass_pair(b200fft_plan& pl, uint32_t N1, uint32_t N2, typename KA::Params& pa, typename KB::Params& pb, uint32_t& FA,
+                                 uint32_t& FB) {
         const uint64_t N = (uint64_t)N1 * N2;
         std::vector<uint32_t> ra, rb;
         if (!smooth_factor(N1, ra) || !smooth_factor(N2, rb)) return false;
-        typename KA::Params pa;
-        typename KB::Params pb;
         if (!fill_smooth_pass<KA>(pl, pa, N1, ra) || !fill_smooth_pass<KB>(pl, pb, N2, rb)) return false;
-        {  // inter-pass twiddles W_N^(k1 n2), [k1][n2], each entry rounded once
-            std::vector<C> t((size_t)N);
-            for (uint64_t k1 = 0; k1 < N1; ++k1)
-                for (uint64_t n2 = 0; n2 < N2; ++n2) t[(size_t)(k1 * N2 + n2)] = hm::twiddle<T>(k1 * n2, N);
-            pb.full_tw = upload(pl, t);
-            if (!pb.full_tw) return false;
-        }
         pa.NN = pb.NN = N;
         pa.other = N2;
         pb.other = N1;
         pa.div_other = make_fastdiv(N2);
         pb.div_other = make_fastdiv(N1);
         // FFTs per CTA: both ping-pong buffers inside 2 * SMOOTH_MAX elements (+ the odd pitch of pass B)
-        const uint32_t FA = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / N1));
+        FA = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / N1));
         const uint32_t pitch = N2 | 1u;
-        const uint32_t FB = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / pitch));
+        FB = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / pitch));
         pa.f_per_cta = FA;
         pa.pitch = N1;
         pa.div_f = make_fastdiv(FA);
@@ -1372,6 +1372,40 @@ struct Builder {
         pb.pitch = pitch;
         pb.div_f = make_fastdiv(FB);
         pb.smem_bytes = rb.size() > 1 ? (uint32_t)(2ull * FB * pitch * sizeof(C)) : 0;
+        return true;
+    }
+    static const C* smooth_full_twiddles(b200fft_plan& pl, uint32_t N1, uint32_t N2) {
+        // inter-pass twiddles W_N^(k1 n2), [k1][n2], each entry rounded once
+        const uint64_t N = (uint64_t)N1 * N2;
+        std::vector<C> t((size_t)N);
+        for (uint64_t k1 = 0; k1 < N1; ++k1)
+            for (uint64_t n2 = 0; n2 < N2; ++n2) t[(size_t)(k1 * N2 + n2)] = hm::twiddle<T>(k1 * n2, N);
+        return upload(pl, t);
+    }
+    // variant 0: SmoothFourStep (the reference's MixedRadix);  1: GoodThomas (N1, N2 coprime: CRT / Ruritanian index maps, no twiddles)
+    template <bool SW>
+    static bool make_smooth_four_step_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
+        using KA = SmoothPassKernel<T, SW, 1>;
+        using KB = SmoothPassKernel<T, SW, 2>;
+        const uint64_t N = (uint64_t)N1 * N2;
+        typename KA::Params pa;
+        typename KB::Params pb;
+        uint32_t FA = 0, FB = 0;
+        if (!smooth_pass_pair<KA, KB>(pl, N1, N2, pa, pb, FA, FB)) return false;
+        if (variant == 1) {
+            // n = crt1[n1] + crt2[n2] mod N is the index with n mod N1 = n1 and n mod N2 = n2
+            const uint64_t e1 = (uint64_t)N2 * hm::invmod(N2 % N1, N1) % N, e2 = (uint64_t)N1 * hm::invmod(N1 % N2, N2) % N;
+            std::vector<uint32_t> c1(N1), c2(N2);
+            for (uint64_t i = 0; i < N1; ++i) c1[(size_t)i] = (uint32_t)(hm::mulmod(i, e1, N));
+            for (uint64_t i = 0; i < N2; ++i) c2[(size_t)i] = (uint32_t)(hm::mulmod(i, e2, N));
+            pa.crt1 = upload(pl, c1);
+            pa.crt2 = upload(pl, c2);
+            if (!pa.crt1 || !pa.crt2) return false;
+            pa.gt = pb.gt = 1;
+        } else {
+            pb.full_tw = smooth_full_twiddles(pl, N1, N2);
+            if (!pb.full_tw) return false;
+        }
         const size_t max_smem = 2ull * (SMOOTH_MAX + 64) * sizeof(C);
         // transforms per chunk: ~32 MiB of intermediate, and FFT indices of a launch must stay below 2^31
         uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / (N * sizeof(C)));
@@ -1398,11 +1432,189 @@ struct Builder {
             }
             return true;
         };
-        pl.desc = "SmoothFourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        pl.desc = std::string(variant == 1 ? "GoodThomas{" : "SmoothFourStep{") + std::to_string(N1) + "x" + std::to_string(N2) + "}";
         return true;
     }
-    static bool make_smooth_four_step(b200fft_plan& pl, uint32_t N1, uint32_t N2) {
-        return pl.direction ? make_smooth_four_step_t<true>(pl, N1, N2) : make_smooth_four_step_t<false>(pl, N1, N2);
+    static bool make_smooth_four_step(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
+        return pl.direction ? make_smooth_four_step_t<true>(pl, N1, N2, variant) : make_smooth_four_step_t<false>(pl, N1, N2, variant);
+    }
+    // coprime split N = N1 * N2 for GoodThomas: both factors <= SMOOTH_MAX and smooth, as balanced as possible
+    static bool coprime_split(uint64_t n, uint32_t& n1, uint32_t& n2) {
+        uint64_t best = 0;
+        for (uint64_t a = 2; a * a <= n; ++a) {
+            if (n % a) continue;
+            const uint64_t b = n / a;
+            if (b > SMOOTH_MAX || hm::gcd(a, b) != 1) continue;
+            std::vector<uint32_t> ra, rb;
+            if (smooth_factor(a, ra) && smooth_factor(b, rb)) best = a;
+        }
+        if (!best) return false;
+        n1 = (uint32_t)best;
+        n2 = (uint32_t)(n / best);
+        return true;
+    }
+
+    // ---------------- SmoothConv: Rader / Bluestein in ONE CTA pass over a smooth inner length (kernels.h) ----------------
+    static constexpr uint32_t CONV_SMOOTH_MAX = sizeof(T) == 4 ? 6144 : 3072;  // 2 M sizeof(C) <= 96 KiB: two CTAs per SM
+    static std::string radix_string(const std::vector<uint32_t>& r) {
+        std::string rs;
+        for (size_t s = 0; s < r.size(); ++s) rs += (s ? "x" : "") + std::to_string(r[s]);
+        return rs;
+    }
+    // mode 0: Rader, pl.len = r0 * p, inner M = p - 1;  mode 1: Bluestein, inner M = pM >= 2 len - 1
+    template <bool SW>
+    static bool make_smooth_conv_t(b200fft_plan& pl, int mode, uint32_t r0, uint32_t pM) {
+        using KT = SmoothConvKernel<T, SW>;
+        const uint32_t n = (uint32_t)pl.len;
+        const uint32_t M = mode == 0 ? pM - 1 : pM;
+        std::vector<uint32_t> radices;
+        if (!smooth_factor(M, radices) || (uint64_t)r0 * M > CONV_SMOOTH_MAX) return false;
+        typename KT::Params base;
+        if (!fill_smooth_pass<KT>(pl, base, M, radices)) return false;
+        base.n = n;
+        base.M = M;
+        base.r0 = r0;
+        base.div_r0 = make_fastdiv(r0);
+        base.mode = mode == 0 ? KT::MODE_RADER : KT::MODE_BLUESTEIN;
+        uint64_t groot = 0;
+        std::vector<C> mult;
+        if (mode == 0) {
+            base.p = pM;
+            std::vector<uint32_t> gpow, ginv;
+            rader_tables(pM, M, gpow, ginv, mult, groot);
+            base.gpow = upload(pl, gpow);
+            base.ginv = upload(pl, ginv);
+            if (!base.gpow || !base.ginv) return false;
+            if (r0 > 1) {
+                std::vector<C> otw((size_t)r0 * pM), wr(r0);
+                for (uint64_t k1 = 0; k1 < r0; ++k1)
+                    for (uint64_t n2 = 0; n2 < pM; ++n2) otw[(size_t)(k1 * pM + n2)] = hm::twiddle<T>(k1 * n2, n);
+                for (uint64_t j = 0; j < r0; ++j) wr[(size_t)j] = hm::twiddle<T>(j, r0);
+                base.otw = upload(pl, otw);
+                base.w_r0 = upload(pl, wr);
+                if (!base.otw || !base.w_r0) return false;
+            }
+        } else {
+            base.p = n;
+            std::vector<C> chirp;
+            bluestein_tables(n, M, chirp, mult);
+            base.chirp = upload(pl, chirp);
+            if (!base.chirp) return false;
+        }
+        base.mult = upload(pl, mult);
+        if (!base.mult) return false;
+        // virtual transforms per CTA: a multiple of r0, both ping-pong buffers inside the budget, at most 64
+        uint32_t F = std::max<uint32_t>(1, CONV_SMOOTH_MAX / M / r0) * r0;
+        while (F > r0 && F > 64) F -= r0;
+        base.f_per_cta = F;
+        base.smem_bytes = (uint32_t)(((2ull * F * M + F) * sizeof(C) + 15) / 16 * 16);
+        const size_t max_smem = (2ull * CONV_SMOOTH_MAX + 64) * sizeof(C) + 16;
+        const uint32_t n_steps = 2 * (uint32_t)radices.size();
+        pl.exec = [=](const ExecCtx& c) {
+            typename KT::Params q = base;
+            q.in = (const C*)c.in;
+            q.out = (C*)c.out;
+            q.n_fft = c.batch;
+            return rt::launch_loop<KT>(q, (c.batch * r0 + F - 1) / F, n_steps, q.smem_bytes, max_smem, c.stream);
+        };
+        pl.launches = [](uint64_t) { return (uint64_t)1; };
+        const std::string inner = "Smooth{" + std::to_string(M) + "=" + radix_string(radices) + "}";
+        if (mode == 0) {
+            const std::string r = "Rader{n=" + std::to_string(pM) + ",g=" + std::to_string(groot) + ",inner=" + inner + ",fused}";
+            pl.desc = r0 > 1 ? "MixedRadix{" + std::to_string(r0) + "x" + r + ",fused}" : r;
+        } else {
+            pl.desc = "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + ",fused}";
+        }
+        return true;
+    }
+    static bool make_smooth_conv(b200fft_plan& pl, int mode, uint32_t r0, uint32_t pM) {
+        return pl.direction ? make_smooth_conv_t<true>(pl, mode, r0, pM) : make_smooth_conv_t<false>(pl, mode, r0, pM);
+    }
+
+    // ---------------- large Rader / Bluestein over a smooth two-pass inner FFT of M = N1 * N2 ----------------
+    // the four launches of make_big_conv (A1 gather|chirp-pad, B1 x mult + conj (+ DC), A2 plain, B2 conj + scatter | conj x chirp)
+    // with the run-time-radix passes: any "easy" prime (p - 1 smooth) above the one-pass limit, Bluestein with the smallest smooth M
+    template <bool SW>
+    static bool make_smooth_big_conv_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
+        using KA = SmoothPassKernel<T, SW, 1>;
+        using KA2 = SmoothPassKernel<T, false, 1>;
+        using KB = SmoothPassKernel<T, SW, 2>;
+        const uint64_t n = pl.len, M = (uint64_t)N1 * N2;
+        typename KA::Params pa;
+        typename KB::Params pb;
+        uint32_t FA = 0, FB = 0;
+        if (!smooth_pass_pair<KA, KB>(pl, N1, N2, pa, pb, FA, FB)) return false;
+        pb.full_tw = smooth_full_twiddles(pl, N1, N2);
+        if (!pb.full_tw) return false;
+        std::vector<C> mult;
+        uint64_t groot = 0;
+        pa.n_outer = pb.n_outer = (uint32_t)n;
+        if (rader) {
+            std::vector<uint32_t> gpow, ginv;
+            rader_tables(n, M, gpow, ginv, mult, groot);
+            pa.gather = upload(pl, gpow);
+            pb.scatter = upload(pl, ginv);
+            if (!pa.gather || !pb.scatter) return false;
+        } else {
+            std::vector<C> chirp;
+            bluestein_tables(n, M, chirp, mult);
+            pa.chirp = pb.chirp = upload(pl, chirp);
+            if (!pa.chirp) return false;
+        }
+        pb.mult = upload(pl, mult);
+        if (!pb.mult) return false;
+        const size_t max_smem = 2ull * (SMOOTH_MAX + 64) * sizeof(C);
+        // two workspaces per chunk inside ~32 MiB; FFT indices of a launch stay below 2^31
+        uint64_t chunk = std::max<uint64_t>(1, (16ull << 20) / (M * sizeof(C)));
+        chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(N1, N2));
+        pl.chunk = chunk;
+        pl.work_bytes = [=](uint64_t batch) { return 2 * std::min(batch, chunk) * M * sizeof(C); };
+        pl.launches = [=](uint64_t batch) { return 4 * ((batch + chunk - 1) / chunk); };
+        pl.exec = [=](const ExecCtx& c) {
+            const C* in = (const C*)c.in;
+            C* out = (C*)c.out;
+            const uint64_t per = std::min(c.batch, chunk) * M;
+            C* w1 = (C*)c.work;
+            C* w2 = w1 + per;
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += chunk) {
+                const uint64_t nb = std::min(chunk, c.batch - b0);
+                typename KA::Params a1 = pa;  // gather | chirp-pad columns -> N1-point FFTs -> w1
+                a1.conv = rader ? 1u : 2u;
+                a1.in = in + b0 * n;
+                a1.out = w1;
+                a1.n_fft = nb * N2;
+                if (!rt::launch_dyn<KA>(a1, (a1.n_fft + FA - 1) / FA, a1.smem_bytes, max_smem, c.stream)) return false;
+                typename KB::Params b1 = pb;  // rows x twiddle -> N2-point FFTs -> x mult, conj (+ DC) -> w2, natural order
+                b1.conv = 1;
+                b1.in = w1;
+                b1.out = w2;
+                b1.x_in = rader ? in + b0 * n : nullptr;
+                b1.x_out = out + b0 * n;
+                b1.n_fft = nb * N1;
+                if (!rt::launch_dyn<KB>(b1, (b1.n_fft + FB - 1) / FB, b1.smem_bytes, max_smem, c.stream)) return false;
+                typename KA2::Params a2;  // plain pass A, in place
+                std::memcpy(&a2, &pa, sizeof(a2));
+                a2.conv = 0;
+                a2.in = w2;
+                a2.out = w2;
+                a2.n_fft = nb * N2;
+                if (!rt::launch_dyn<KA2>(a2, (a2.n_fft + FA - 1) / FA, a2.smem_bytes, max_smem, c.stream)) return false;
+                typename KB::Params b2 = pb;  // rows x twiddle -> N2-point FFTs -> conj + scatter | conj x chirp -> out
+                b2.conv = rader ? 2u : 3u;
+                b2.in = w2;
+                b2.out = out + b0 * n;
+                b2.n_fft = nb * N1;
+                if (!rt::launch_dyn<KB>(b2, (b2.n_fft + FB - 1) / FB, b2.smem_bytes, max_smem, c.stream)) return false;
+            }
+            return true;
+        };
+        const std::string inner = "SmoothFourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        pl.desc = rader ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + "}"
+                        : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + "}";
+        return true;
+    }
+    static bool make_smooth_big_conv(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
+        return pl.direction ? make_smooth_big_conv_t<true>(pl, N1, N2, rader) : make_smooth_big_conv_t<false>(pl, N1, N2, rader);
     }
 
     // ---------------- Bluestein (fused) ----------------
@@ -1417,7 +1629,7 @@ struct Builder {
             c[(size_t)i] = cj;
             if (i) c[(size_t)(M - i)] = cj;
         }
-        hm::fft_pow2_ld(c);
+        if (hm::is_pow2(M)) hm::fft_pow2_ld(c); else hm::fft_any_ld(c);
         mult.resize((size_t)M);
         for (uint64_t i = 0; i < M; ++i) mult[(size_t)i] = mk<T>((T)c[(size_t)i].x, (T)c[(size_t)i].y);
     }
@@ -1485,7 +1697,7 @@ struct Builder {
             gpow[(size_t)i] = (uint32_t)a;
             ginv[(size_t)i] = (uint32_t)b;
         }
-        hm::fft_pow2_ld(d);
+        if (hm::is_pow2(M)) hm::fft_pow2_ld(d); else hm::fft_any_ld(d);
         mult.resize((size_t)M);
         for (size_t i = 0; i < (size_t)M; ++i) mult[i] = mk<T>((T)d[i].x, (T)d[i].y);
     }
@@ -1533,9 +1745,163 @@ struct Builder {
         return false;
     }
 
+    static bool smooth_factor_any(uint64_t n) {
+        std::vector<uint32_t> r;
+        return smooth_factor(n, r);
+    }
+    // smallest M = 2^a 3^b 5^c 7^d >= lo that the smooth kernels can run (one pass, or a two-pass split); 0 = none
+    static uint64_t bluestein_smooth_len(uint64_t lo) {
+        std::vector<uint64_t> cand;
+        const uint64_t hi = 2 * lo;  // (the next power of two is below this)
+        for (uint64_t a = 1; a < hi; a *= 7)
+            for (uint64_t b = a; b < hi; b *= 5)
+                for (uint64_t c = b; c < hi; c *= 3)
+                    for (uint64_t d = c; d < hi; d *= 2)
+                        if (d >= lo) cand.push_back(d);
+        std::sort(cand.begin(), cand.end());
+        for (uint64_t d : cand) {
+            uint32_t s1 = 0, s2 = 0;
+            if (d <= CONV_SMOOTH_MAX ? smooth_factor_any(d) : smooth_split(d, s1, s2)) return d;
+        }
+        return 0;
+    }
+    // B200FFT_GENERAL_RADER=0: primes other than the Fermat ones go through Bluestein, as in round 1 (A/B measurements)
+    static bool use_general_rader() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_GENERAL_RADER");
+            return !(e && std::atoi(e) == 0);
+        }();
+        return v;
+    }
+    // B200FFT_GOOD_THOMAS=1: coprime two-pass splits run as GoodThomas (index maps, no twiddle table) instead of SmoothFourStep
+    static bool use_good_thomas() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_GOOD_THOMAS");
+            return e && std::atoi(e) == 1;
+        }();
+        return v;
+    }
+    // B200FFT_BLUESTEIN_SMOOTH_BIG=1: also above the one-pass limit (four run-time-radix passes over the smooth length instead of
+    // four compiled passes over the next power of two); otherwise reachable through a recipe only
+    static bool bluestein_smooth_big() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_BLUESTEIN_SMOOTH_BIG");
+            return e && std::atoi(e) == 1;
+        }();
+        return v;
+    }
+    static uint64_t bluestein_smooth_pct() {
+        static uint64_t v = [] {
+            const char* e = std::getenv("B200FFT_BLUESTEIN_SMOOTH");
+            return e ? (uint64_t)std::atoi(e) : (uint64_t)70;
+        }();
+        return v;
+    }
+
     // ---------------- top level ----------------
+    // a caller-supplied recipe (include/b200fft.h): node 0 is the root; every structural claim of the recipe is checked
+    static int build_from_recipe(b200fft_plan& pl) {
+        const std::vector<b200fft_recipe_node>& rc = pl.recipe;
+        const b200fft_recipe_node& r = rc[0];
+        const uint64_t n = pl.len;
+        auto unsupported = [](const std::string& m) { return fail(B200FFT_ERR_UNSUPPORTED, "recipe: " + m); };
+        auto child_of = [&](const b200fft_recipe_node& nd) -> const b200fft_recipe_node* {
+            return (nd.child > 0 && nd.child < rc.size()) ? &rc[nd.child] : nullptr;
+        };
+        bool ok = false;
+        switch (r.kind) {
+            case B200FFT_RECIPE_POW2:
+                if (!hm::is_pow2(n)) return unsupported("POW2 needs a power-of-two length");
+                if (n <= DirectMax<T>::v) ok = make_direct_rt(pl, (uint32_t)n);
+                else if (n <= (uint64_t)TILE_MAX * TILE_MAX) ok = make_four_step(pl, hm::ilog2(n));
+                else return unsupported("power-of-two lengths above 2^24");
+                break;
+            case B200FFT_RECIPE_SMOOTH: {
+                std::vector<uint32_t> radices;
+                if (n > SMOOTH_MAX || !smooth_factor(n, radices)) return unsupported("SMOOTH needs prime factors <= 31 and a one-pass length");
+                ok = smooth_dispatch(pl, 0, 0, 0);
+                break;
+            }
+            case B200FFT_RECIPE_MIXED_RADIX:
+            case B200FFT_RECIPE_GOOD_THOMAS: {
+                uint64_t a = std::min(r.a, r.b), b = std::max(r.a, r.b);
+                if (a < 2 || a * b != n) return unsupported("the split must multiply to the length");
+                if (r.kind == B200FFT_RECIPE_GOOD_THOMAS && hm::gcd(a, b) != 1) return unsupported("GOOD_THOMAS needs a coprime split");
+                if (hm::is_pow2(n) && r.kind == B200FFT_RECIPE_MIXED_RADIX) {
+                    const uint32_t lg = hm::ilog2(n);
+                    if (a != (1ull << (lg / 2)) || n <= DirectMax<T>::v) return unsupported("power-of-two MIXED_RADIX must be the balanced two-pass split");
+                    ok = make_four_step(pl, lg);
+                    break;
+                }
+                if (b > SMOOTH_MAX || !smooth_factor_any(a) || !smooth_factor_any(b)) return unsupported("both factors must be smooth one-pass lengths");
+                ok = smooth_dispatch(pl, r.kind == B200FFT_RECIPE_GOOD_THOMAS ? 4 : 1, (uint32_t)a, (uint32_t)b);
+                break;
+            }
+            case B200FFT_RECIPE_RADER: {
+                const uint64_t r0 = r.a > 1 ? r.a : 1;
+                if (n % r0 || !hm::is_prime(n / r0) || n / r0 < 3) return unsupported("RADER needs len = a * prime");
+                const uint64_t p = n / r0, M = p - 1;
+                const b200fft_recipe_node* in = child_of(r);
+                if (in && in->len != M) return unsupported("the inner FFT of RADER has length p - 1");
+                const uint32_t ik = in ? in->kind : (uint32_t)B200FFT_RECIPE_AUTO;
+                uint32_t s1 = 0, s2 = 0;
+                if (hm::is_pow2(M) && r0 == 1 && (ik == B200FFT_RECIPE_AUTO || ik == B200FFT_RECIPE_POW2 || ik == B200FFT_RECIPE_MIXED_RADIX)) {
+                    if (M <= 256) ok = make_rader_rt(pl, (uint32_t)M);
+                    else if (M <= (uint64_t)TILE_MAX * TILE_MAX && M >= (uint64_t)TILE_MIN * TILE_MIN) ok = make_big_conv(pl, M, true);
+                    else return unsupported("RADER over this power-of-two length");
+                } else if ((ik == B200FFT_RECIPE_AUTO || ik == B200FFT_RECIPE_SMOOTH) && r0 <= 8 && r0 * M <= CONV_SMOOTH_MAX && smooth_factor_any(M)) {
+                    ok = smooth_dispatch(pl, 2, (uint32_t)r0, (uint32_t)p);
+                } else if (r0 == 1 && (ik == B200FFT_RECIPE_AUTO || ik == B200FFT_RECIPE_MIXED_RADIX) && smooth_factor_any(M)) {
+                    if (in && ik == B200FFT_RECIPE_MIXED_RADIX) {
+                        s1 = (uint32_t)std::min(in->a, in->b);
+                        s2 = (uint32_t)std::max(in->a, in->b);
+                        if ((uint64_t)s1 * s2 != M || s2 > SMOOTH_MAX || !smooth_factor_any(s1) || !smooth_factor_any(s2))
+                            return unsupported("inner split of RADER");
+                    } else if (!smooth_split(M, s1, s2)) {
+                        return unsupported("RADER: p - 1 has no two-pass split");
+                    }
+                    ok = smooth_dispatch(pl, 5, s1, s2);
+                } else {
+                    return unsupported("RADER: p - 1 must factor into primes <= 31");
+                }
+                break;
+            }
+            case B200FFT_RECIPE_BLUESTEIN: {
+                const b200fft_recipe_node* in = child_of(r);
+                const uint64_t M = in ? in->len : hm::next_pow2(2 * n - 1);
+                if (n < 2 || M < 2 * n - 1) return unsupported("the inner FFT of BLUESTEIN needs length >= 2 len - 1");
+                const uint32_t ik = in ? in->kind : (uint32_t)B200FFT_RECIPE_AUTO;
+                uint32_t s1 = 0, s2 = 0;
+                if (hm::is_pow2(M) && ik != B200FFT_RECIPE_SMOOTH) {
+                    if (M <= FUSED_CONV_MAX) ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
+                    else if (M <= (uint64_t)TILE_MAX * TILE_MAX) ok = make_big_conv(pl, M, false);
+                    else return unsupported("BLUESTEIN over this power-of-two length");
+                } else if (M <= CONV_SMOOTH_MAX && smooth_factor_any(M) && ik != B200FFT_RECIPE_MIXED_RADIX) {
+                    ok = smooth_dispatch(pl, 3, (uint32_t)M, 0);
+                } else if (smooth_factor_any(M)) {
+                    if (in && ik == B200FFT_RECIPE_MIXED_RADIX && in->a * in->b == M) {
+                        s1 = (uint32_t)std::min(in->a, in->b);
+                        s2 = (uint32_t)std::max(in->a, in->b);
+                        if (s2 > SMOOTH_MAX || !smooth_factor_any(s1) || !smooth_factor_any(s2)) return unsupported("inner split of BLUESTEIN");
+                    } else if (!smooth_split(M, s1, s2)) {
+                        return unsupported("BLUESTEIN: the inner length has no two-pass split");
+                    }
+                    ok = smooth_dispatch(pl, 6, s1, s2);
+                } else {
+                    return unsupported("BLUESTEIN: the inner length must be a power of two or factor into primes <= 31");
+                }
+                break;
+            }
+            default:
+                return fail(B200FFT_ERR_INVALID_ARG, "recipe: unknown node kind");
+        }
+        if (!ok) return fail(B200FFT_ERR_CUDA, "plan construction failed: " + rt::last_error());
+        return B200FFT_OK;
+    }
+
     static int build(b200fft_plan& pl) {
         const uint64_t n = pl.len;
+        if (!pl.recipe.empty() && pl.recipe[0].kind != B200FFT_RECIPE_AUTO && n > 1) return build_from_recipe(pl);
         if (n <= 1) {
             pl.exec = [n](const ExecCtx& c) {
                 if (n == 0 || c.in == c.out || c.batch == 0) return true;
@@ -1558,6 +1924,8 @@ struct Builder {
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^24 are not planned by this build");
         } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
             ok = smooth_dispatch(pl, 0, 0, 0);  // every prime factor <= 31
+        } else if (uint32_t g1 = 0, g2 = 0; use_good_thomas() && n > SMOOTH_MAX && coprime_split(n, g1, g2)) {
+            ok = smooth_dispatch(pl, 4, g1, g2);  // opt-in (B200FFT_GOOD_THOMAS=1): coprime split, no inter-pass twiddles
         } else if (uint32_t s1 = 0, s2 = 0; n > SMOOTH_MAX && n <= (1ull << 23) && smooth_split(n, s1, s2)) {
             ok = smooth_dispatch(pl, 1, s1, s2);  // composite of small primes: two passes instead of Bluestein's four
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
@@ -1565,14 +1933,33 @@ struct Builder {
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {
             ok = make_big_conv(pl, n - 1, true);  // 65537
         } else {
-            const uint64_t M = hm::next_pow2(2 * n - 1);
-            if (M <= FUSED_CONV_MAX)
-                ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
-            else if (M <= (uint64_t)TILE_MAX * TILE_MAX)
-                ok = make_big_conv(pl, M, false);
-            else
-                return fail(B200FFT_ERR_UNSUPPORTED,
-                            "non-power-of-two lengths above 2^23 are not planned by this build");
+            // what is left has a prime factor p > 31.  The reference's rule (src/plan.rs:636-664): Rader when p - 1 factors into small
+            // primes ("easy" prime), else Bluestein -- with the freedom to pick any inner length >= 2n - 1.
+            const uint64_t p = hm::largest_prime_factor(n), r0 = n / p;
+            std::vector<uint32_t> rr;
+            uint32_t b1 = 0, b2 = 0;
+            if (use_general_rader() && r0 <= 8 && r0 * (p - 1) <= CONV_SMOOTH_MAX && smooth_factor(p - 1, rr)) {
+                ok = smooth_dispatch(pl, 2, (uint32_t)r0, (uint32_t)p);  // one CTA pass: MixedRadix{r0 x Rader(p)} fused
+            } else if (use_general_rader() && r0 == 1 && smooth_factor_any(p - 1) && smooth_split(p - 1, b1, b2)) {
+                ok = smooth_dispatch(pl, 5, b1, b2);  // easy prime above the one-pass limit: four passes over n - 1
+            } else {
+                const uint64_t M2 = hm::next_pow2(2 * n - 1);
+                const uint64_t M3 = bluestein_smooth_len(2 * n - 1);
+                // the run-time-radix kernels cost more per point than the compiled power-of-two ones: the smooth length must
+                // be clearly shorter to win (B200FFT_BLUESTEIN_SMOOTH = percentage of M2 it must stay below; 0 = never)
+                const bool smooth_wins = M3 != 0 && M3 * 100 <= M2 * bluestein_smooth_pct();
+                if (smooth_wins && M3 <= CONV_SMOOTH_MAX)
+                    ok = smooth_dispatch(pl, 3, (uint32_t)M3, 0);
+                else if (M2 <= FUSED_CONV_MAX)
+                    ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M2, 8));
+                else if (smooth_wins && M3 > CONV_SMOOTH_MAX && bluestein_smooth_big() && smooth_split(M3, b1, b2))
+                    ok = smooth_dispatch(pl, 6, b1, b2);  // opt-in: the run-time-radix passes are slower per byte than the compiled ones
+                else if (M2 <= (uint64_t)TILE_MAX * TILE_MAX)
+                    ok = make_big_conv(pl, M2, false);
+                else
+                    return fail(B200FFT_ERR_UNSUPPORTED,
+                                "non-power-of-two lengths above 2^23 are not planned by this build");
+            }
         }
         if (!ok) return fail(B200FFT_ERR_CUDA, "plan construction failed: " + rt::last_error());
         return B200FFT_OK;
@@ -1967,6 +2354,34 @@ int b200fft_plan_create(b200fft_plan** out, uint64_t len, int direction, int pre
     pl->direction = direction;
     pl->precision = precision;
     pl->device = device;
+    const int rc = precision == B200FFT_F32 ? b2::build_plan_f32(*pl) : b2::build_plan_f64(*pl);
+    if (rc != B200FFT_OK) return rc;
+    *out = pl.release();
+    return B200FFT_OK;
+}
+
+int b200fft_plan_create_from_recipe(b200fft_plan** out, const b200fft_recipe_node* nodes, uint32_t n_nodes, int direction, int precision,
+                                    int device) {
+    if (!out) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (!nodes || n_nodes == 0 || n_nodes > 64) return b2::fail(B200FFT_ERR_INVALID_ARG, "recipe: 1..64 nodes expected");
+    if ((direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) || (precision != B200FFT_F32 && precision != B200FFT_F64))
+        return b2::fail(B200FFT_ERR_INVALID_ARG, "unknown direction or precision");
+    for (uint32_t i = 0; i < n_nodes; ++i)
+        if (nodes[i].child >= n_nodes || (nodes[i].child != 0 && nodes[i].child <= i))
+            return b2::fail(B200FFT_ERR_INVALID_ARG, "recipe: child indices must point forward inside the node array");
+    const int ndev = b2::rt::device_count();
+    if (ndev <= 0) return b2::fail(B200FFT_ERR_NO_DEVICE, "no sm_100 CUDA device is visible (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return b2::fail(B200FFT_ERR_INVALID_ARG, "device index out of range");
+    if (!b2::rt::set_device(device)) return b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    std::unique_ptr<b200fft_plan> pl(new b200fft_plan());
+    pl->len = nodes[0].len;
+    pl->direction = direction;
+    pl->precision = precision;
+    pl->device = device;
+    pl->recipe.assign(nodes, nodes + n_nodes);
+    if (!b2::hm::is_pow2(pl->len) && pl->len > (1ull << 23))
+        return b2::fail(B200FFT_ERR_UNSUPPORTED, "non-power-of-two lengths above 2^23 are not planned by this build");
     const int rc = precision == B200FFT_F32 ? b2::build_plan_f32(*pl) : b2::build_plan_f64(*pl);
     if (rc != B200FFT_OK) return rc;
     *out = pl.release();

@@ -674,6 +674,26 @@ struct SmoothPassKernel {
         FastDiv div_t[MAX_STAGES];  // by T_s = n / radix[s]
         FastDiv div_p[MAX_STAGES];  // by p_s = product of the radices before s
         FastDiv div_other, div_f;
+        // --- variants of the same two passes (0 / null = the plain SmoothFourStep) ---
+        // Good-Thomas (src/algorithm/good_thomas_algorithm.rs:144-248): N1, N2 coprime, no inter-pass twiddles (full_tw = null);
+        // pass A reads x[crt1[n1] + crt2[n2] mod N] (the CRT map: n = n1 mod N1, n = n2 mod N2), pass B writes
+        // X[(k1 N2 + k2 N1) mod N] (the Ruritanian map) -- the reference's reindex_input / reindex_output folded into the passes
+        const uint32_t* crt1;  // N1 entries: n1 * N2 * (N2^-1 mod N1) mod N
+        const uint32_t* crt2;  // N2 entries: n2 * N1 * (N1^-1 mod N2) mod N
+        uint32_t gt;
+        // large Rader / Bluestein plans over a smooth inner length M = N1 * N2 (the passes of LoadColsConv / StoreTransposedConv):
+        //   MODE 1, conv 1: inner element i = e N2 + c comes from in[b n_outer + gather[i]]                       (Rader)
+        //   MODE 1, conv 2: i < n_outer ? in[b n_outer + i] * chirp[i] : 0                                        (Bluestein)
+        //   MODE 2, conv 1: end of inner FFT #1 -- out[b M + k] = conj(v * mult[k]) (+ Rader DC when x_in != null)
+        //   MODE 2, conv 2: out[b n_outer + scatter[k]] = conj(v)                                                 (Rader)
+        //   MODE 2, conv 3: k < n_outer: out[b n_outer + k] = conj(v) * chirp[k]                                  (Bluestein)
+        uint32_t conv, n_outer;
+        const uint32_t* gather;
+        const uint32_t* scatter;
+        const cx<T>* chirp;
+        const cx<T>* mult;
+        const cx<T>* x_in;
+        cx<T>* x_out;
     };
     struct Regs {};
 
@@ -707,13 +727,43 @@ struct SmoothPassKernel {
             const uint32_t k = i - p.div_p[s].div(i) * pp;
             cx<T> a[R];
             if (first) {
-                if (MODE == 1) {
+                if (MODE == 1 && p.gt) {
+                    const cx<T>* src = p.in + (uint64_t)b * p.NN;
+                    const uint32_t o2 = ldg_u32(p.crt2 + c);
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) {
+                        uint32_t o = ldg_u32(p.crt1 + i + (uint32_t)q * T_s) + o2;
+                        if (o >= (uint32_t)p.NN) o -= (uint32_t)p.NN;
+                        const cx<T> v = src[o];
+                        a[q] = SW ? swap_ri(v) : v;
+                    }
+                } else if (MODE == 1 && p.conv) {
+                    const cx<T>* src = p.in + (uint64_t)b * p.n_outer;
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) {
+                        const uint32_t ii = (i + (uint32_t)q * T_s) * p.other + c;  // inner index e N2 + c
+                        cx<T> v = mk<T>(0, 0);
+                        if (p.conv == 1) {
+                            v = src[ldg_u32(p.gather + ii)];
+                            if (SW) v = swap_ri(v);
+                        } else if (ii < p.n_outer) {
+                            v = ld_stream(src + ii);
+                            if (SW) v = swap_ri(v);
+                            v = cmul(v, ldg(p.chirp + ii));
+                        }
+                        a[q] = v;
+                    }
+                } else if (MODE == 1) {
                     const cx<T>* src = p.in + (uint64_t)b * p.NN + c;
                     B2_UNROLL
                     for (int q = 0; q < R; ++q) {
                         const cx<T> v = ld_cs(src + (uint64_t)(i + (uint32_t)q * T_s) * p.other);
                         a[q] = SW ? swap_ri(v) : v;
                     }
+                } else if (p.full_tw == nullptr) {  // Good-Thomas: no inter-pass twiddles
+                    const cx<T>* src = p.in + g * (uint64_t)p.n + i;
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) a[q] = ld_cs(src + (size_t)q * T_s);
                 } else {
                     const cx<T>* src = p.in + g * (uint64_t)p.n + i;
                     const cx<T>* t = p.full_tw + (uint64_t)c * p.n + i;
@@ -728,7 +778,38 @@ struct SmoothPassKernel {
             }
             Bfly<R, T>::run(a);
             const uint32_t base = (i - k) * R + k;
-            if (last) {
+            if (last && MODE == 2 && p.gt) {
+                cx<T>* dst = p.out + (uint64_t)b * p.NN;
+                const uint32_t o1 = c * p.n;  // k1 N2
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) {
+                    uint32_t o = o1 + (base + (uint32_t)m * pp) * p.other;  // + k2 N1
+                    if (o >= (uint32_t)p.NN) o -= (uint32_t)p.NN;
+                    dst[o] = SW ? swap_ri(a[m]) : a[m];
+                }
+            } else if (last && MODE == 2 && p.conv) {
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) {
+                    const uint32_t kk = c + (base + (uint32_t)m * pp) * p.other;  // inner output index k1 + N1 k2
+                    if (p.conv == 1) {
+                        cx<T> w = conj(cmul(a[m], ldg(p.mult + kk)));
+                        if (p.x_in != nullptr && kk == 0) {
+                            cx<T> x0 = p.x_in[(uint64_t)b * p.n_outer];
+                            if (SW) x0 = swap_ri(x0);
+                            const cx<T> dc = x0 + a[m];
+                            p.x_out[(uint64_t)b * p.n_outer] = SW ? swap_ri(dc) : dc;
+                            w = w + conj(x0);
+                        }
+                        p.out[(uint64_t)b * p.NN + kk] = w;
+                    } else if (p.conv == 2) {
+                        const cx<T> w = conj(a[m]);
+                        p.out[(uint64_t)b * p.n_outer + ldg_u32(p.scatter + kk)] = SW ? swap_ri(w) : w;
+                    } else if (kk < p.n_outer) {
+                        const cx<T> w = cmul(conj(a[m]), ldg(p.chirp + kk));
+                        st_stream(p.out + (uint64_t)b * p.n_outer + kk, SW ? swap_ri(w) : w);
+                    }
+                }
+            } else if (last) {
                 cx<T>* dst = p.out + (uint64_t)b * p.NN + c;
                 B2_UNROLL
                 for (int m = 0; m < R; ++m) {
@@ -764,6 +845,176 @@ struct SmoothPassKernel {
             default: break;
         }
     }
+};
+
+// ------------------------------------------------------------------------------------------
+// SmoothConvKernel: a whole convolution-based transform in ONE CTA pass over a SMOOTH inner length M (prime factors
+// <= 31, run-time radix list as in SmoothKernel):
+//   MODE_RADER      prime p = M + 1 (src/algorithm/raders_algorithm.rs:235-283): gather by g^(i+1) -> FFT_M -> DC, x D, conj
+//                   -> FFT_M -> conj, scatter by g^-(i+1).  This is what makes every "easy" prime (p - 1 smooth -- the
+//                   reference's rule, src/plan.rs:129,636-664) a one-pass plan instead of a Bluestein over 2-4x the data.
+//                   With an OUTER radix r0 > 1 the transform length is n = r0 * p and the kernel is the reference's
+//                   MixedRadix{r0 x Rader(p)} (src/plan.rs:412-425; e.g. 1234 = 2 x Rader(617)) fused: virtual
+//                   transform (t, k1) runs Rader on u[n2] = W_n^(n2 k1) * sum_n1 x_t[n1 p + n2] W_r0^(n1 k1), its result k2
+//                   lands on X_t[k1 + r0 k2].
+//   MODE_BLUESTEIN  any n with 2n - 1 <= M (src/algorithm/bluesteins_algorithm.rs:100-136): x * chirp, zero pad -> FFT_M
+//                   -> x mult, conj -> FFT_M -> conj * chirp; lets M be the smallest 2^a 3^b 5^c 7^d instead of the next
+//                   power of two (the idea of src/plan.rs:649-657 and src/avx/avx_planner.rs:945-994).
+// 2 S steps (S = stages of the M-point FFT) over a ping-pong pair of shared-memory buffers, a CTA barrier between steps;
+// step 0 reads global memory, step S - 1 does the DC bookkeeping, step S applies the pointwise multiply on its loads,
+// step 2 S - 1 writes global memory.  The step index is run-time data (run_kernel_loop): 14 butterfly bodies per
+// precision instead of 14 x 16.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SW>
+struct SmoothConvKernel {
+    using T_ = T;
+    static constexpr int NT = 256;
+    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MAX_STAGES = 8;
+    static constexpr int NPHASE = 2 * MAX_STAGES;  // CPU replay: phase<P> = step P
+    static constexpr size_t SMEM_BYTES = 0;        // run-time sized: Params::smem_bytes
+    static constexpr uint32_t MODE_RADER = 0, MODE_BLUESTEIN = 1;
+    struct Params {
+        const cx<T>* in;
+        cx<T>* out;
+        const cx<T>* tw;        // packed stage twiddles of the M-point FFT (layout as in SmoothKernel)
+        const cx<T>* mult;      // M entries
+        const uint32_t* gpow;   // Rader: g^(i+1) mod p
+        const uint32_t* ginv;   // Rader: g^-(i+1) mod p
+        const cx<T>* chirp;     // Bluestein: W_2n^(i^2), n entries
+        const cx<T>* otw;       // r0 > 1: W_n^(n2 k1), [k1][n2] (r0 x p entries)
+        const cx<T>* w_r0;      // r0 > 1: W_r0^j, r0 entries
+        uint64_t n_fft;         // transforms of length n in this launch
+        uint32_t n;             // transform length (Rader: r0 * p)
+        uint32_t p;             // Rader: the prime (M + 1)
+        uint32_t M, r0, mode;
+        uint32_t n_stages, f_per_cta, smem_bytes;  // f_per_cta = VIRTUAL transforms per CTA (a multiple of r0)
+        uint32_t radix[MAX_STAGES];
+        uint32_t tw_off[MAX_STAGES];
+        FastDiv div_t[MAX_STAGES];  // by T_s = M / radix[s]
+        FastDiv div_p[MAX_STAGES];  // by p_s = product of the radices before s
+        FastDiv div_r0;
+    };
+    struct Regs {};
+
+    static B2_HD cx<T> ld_in(const Params& p, uint64_t off) {
+        const cx<T> v = ld_stream(p.in + off);
+        return SW ? swap_ri(v) : v;
+    }
+    // Rader input of virtual transform (t, k1) at n2: the outer radix-r0 butterfly and its twiddle, folded into the load
+    static B2_HD cx<T> u_at(const Params& p, uint64_t t, uint32_t k1, uint32_t n2) {
+        const uint64_t base = t * (uint64_t)p.n + n2;
+        if (p.r0 == 1) return ld_in(p, base);
+        cx<T> acc = ld_in(p, base);
+        uint32_t j = 0;
+        for (uint32_t n1 = 1; n1 < p.r0; ++n1) {
+            j += k1;
+            if (j >= p.r0) j -= p.r0;
+            acc = acc + cmul(ld_in(p, base + (uint64_t)n1 * p.p), ldg(p.w_r0 + j));
+        }
+        return k1 ? cmul(acc, ldg(p.otw + (size_t)k1 * p.p + n2)) : acc;
+    }
+
+    template <int R>
+    static B2_HD void stage(const Params& p, uint32_t bid, int tid, uint32_t step, cx<T>* smem) {
+        const uint32_t S = p.n_stages, M = p.M, F = p.f_per_cta;
+        const bool second = step >= S;
+        const uint32_t s = second ? step - S : step;
+        const bool first_s = (s == 0), last_s = (s == S - 1);
+        const uint32_t pp = p.div_p[s].d, T_s = p.div_t[s].d;
+        const cx<T>* src_buf = smem + (size_t)((step + 1) & 1) * F * M;
+        cx<T>* dst_buf = smem + (size_t)(step & 1) * F * M;
+        cx<T>* u0s = smem + (size_t)2 * F * M;  // Rader: u[0] of every virtual transform of the CTA
+        const cx<T>* tws = p.tw + p.tw_off[s];
+        const bool rader = p.mode == MODE_RADER;
+        for (uint32_t b = (uint32_t)tid; b < F * T_s; b += NT) {
+            const uint32_t f = p.div_t[s].div(b), i = b - f * T_s;
+            const uint64_t gv = (uint64_t)bid * F + f;
+            const uint64_t t = p.r0 == 1 ? gv : (uint64_t)p.div_r0.div((uint32_t)gv);
+            if (t >= p.n_fft) continue;
+            const uint32_t k1 = (uint32_t)(gv - t * p.r0);
+            const uint32_t k = i - p.div_p[s].div(i) * pp;
+            cx<T> a[R];
+            if (first_s && !second) {
+                B2_UNROLL
+                for (int q = 0; q < R; ++q) {
+                    const uint32_t idx = i + (uint32_t)q * T_s;
+                    if (rader) {
+                        a[q] = u_at(p, t, k1, ldg_u32(p.gpow + idx));
+                    } else {
+                        a[q] = idx < p.n ? cmul(ld_in(p, t * (uint64_t)p.n + idx), ldg(p.chirp + idx)) : mk<T>(0, 0);
+                    }
+                }
+                if (rader && i == 0) u0s[f] = u_at(p, t, k1, 0);  // (the same thread owns output 0 of every stage)
+            } else {
+                const cx<T>* src = src_buf + (size_t)f * M + i;
+                B2_UNROLL
+                for (int q = 0; q < R; ++q) a[q] = src[(size_t)q * T_s];
+                if (first_s) {  // first stage of the second FFT: pointwise multiply + conjugate on the way in
+                    B2_UNROLL
+                    for (int q = 0; q < R; ++q) a[q] = conj(cmul(a[q], ldg(p.mult + i + (uint32_t)q * T_s)));
+                    if (rader && i == 0) a[0] = a[0] + conj(u0s[f]);
+                } else {
+                    B2_UNROLL
+                    for (int q = 1; q < R; ++q) a[q] = cmul(a[q], ldg(tws + (size_t)(q - 1) * pp + k));
+                }
+            }
+            Bfly<R, T>::run(a);
+            const uint32_t base = (i - k) * R + k;
+            if (last_s && second) {
+                if (rader) {
+                    cx<T>* dst = p.out + t * (uint64_t)p.n + k1;
+                    B2_UNROLL
+                    for (int m = 0; m < R; ++m) {
+                        const cx<T> v = conj(a[m]);
+                        dst[(size_t)p.r0 * ldg_u32(p.ginv + base + (uint32_t)m * pp)] = SW ? swap_ri(v) : v;
+                    }
+                } else {
+                    cx<T>* dst = p.out + t * (uint64_t)p.n;
+                    B2_UNROLL
+                    for (int m = 0; m < R; ++m) {
+                        const uint32_t o = base + (uint32_t)m * pp;
+                        if (o < p.n) {
+                            const cx<T> v = cmul(conj(a[m]), ldg(p.chirp + o));
+                            st_stream(dst + o, SW ? swap_ri(v) : v);
+                        }
+                    }
+                }
+            } else {
+                cx<T>* dst = dst_buf + (size_t)f * M + base;
+                B2_UNROLL
+                for (int m = 0; m < R; ++m) dst[(size_t)m * pp] = a[m];
+                if (last_s && rader && i == 0) {  // X[0] = u[0] + sum of the rest (raders_algorithm.rs:252-262)
+                    const cx<T> dc = u0s[f] + a[0];
+                    p.out[t * (uint64_t)p.n + k1] = SW ? swap_ri(dc) : dc;
+                }
+            }
+        }
+    }
+
+    static B2_HD void step(const Params& p, uint32_t bid, int tid, uint32_t st, cx<T>* smem) {
+        if (st >= 2 * p.n_stages) return;
+        const uint32_t s = st >= p.n_stages ? st - p.n_stages : st;
+        switch (p.radix[s]) {
+            case 2: stage<2>(p, bid, tid, st, smem); break;
+            case 3: stage<3>(p, bid, tid, st, smem); break;
+            case 4: stage<4>(p, bid, tid, st, smem); break;
+            case 5: stage<5>(p, bid, tid, st, smem); break;
+            case 7: stage<7>(p, bid, tid, st, smem); break;
+            case 8: stage<8>(p, bid, tid, st, smem); break;
+            case 16: stage<16>(p, bid, tid, st, smem); break;
+            case 11: stage<11>(p, bid, tid, st, smem); break;
+            case 13: stage<13>(p, bid, tid, st, smem); break;
+            case 17: stage<17>(p, bid, tid, st, smem); break;
+            case 19: stage<19>(p, bid, tid, st, smem); break;
+            case 23: stage<23>(p, bid, tid, st, smem); break;
+            case 29: stage<29>(p, bid, tid, st, smem); break;
+            case 31: stage<31>(p, bid, tid, st, smem); break;
+            default: break;
+        }
+    }
+    template <int P>
+    static B2_HD void phase(const Params& p, uint32_t bid, int tid, Regs&, cx<T>* smem) { step(p, bid, tid, (uint32_t)P, smem); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1249,6 +1500,18 @@ __global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_dyn(const _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename KT::Regs r;
     PhaseRunner<KT, 0>::run(p, blockIdx.x, (int)threadIdx.x, r, reinterpret_cast<cx<typename KT::T_>*>(smem_raw));
+}
+
+// kernels whose steps are run-time data (SmoothConvKernel): step(p, bid, tid, st, smem) for st = 0 .. n_steps - 1 with a
+// CTA barrier in between
+template <class KT>
+__global__ void __launch_bounds__(KT::NT, KT::MIN_BLOCKS) run_kernel_loop(const __grid_constant__ typename KT::Params p, uint32_t n_steps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<typename KT::T_>* smem = reinterpret_cast<cx<typename KT::T_>*>(smem_raw);
+    for (uint32_t st = 0; st < n_steps; ++st) {
+        KT::step(p, blockIdx.x, (int)threadIdx.x, st, smem);
+        if (st + 1 < n_steps) __syncthreads();
+    }
 }
 
 // Thread 0's bookkeeping next to the tiles (all of it off the tiles' critical path):

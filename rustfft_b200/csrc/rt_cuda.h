@@ -57,7 +57,25 @@ static bool d2d_async(void* dst, const void* src, size_t n, stream_t s) {
     return check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync D2D");
 }
 static bool memset_async(void* d, int v, size_t n, stream_t s) { return check(cudaMemsetAsync(d, v, n, s), "cudaMemsetAsync"); }
+// The default pool returns freed memory to the OS at the next synchronisation point, so a caller that synchronises
+// between two execs paid a fresh multi-millisecond allocation for the same workspace every time (the 0.68 <-> 3.9 ms
+// bimodal timing of the 65537-point plan in round 1).  The pool keeps what it has been given: one threshold per device.
+static void keep_pool_memory() {
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (configured.load(std::memory_order_acquire) & bit) return;
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    configured.fetch_or(bit, std::memory_order_release);
+}
 static void* malloc_async(size_t bytes, stream_t s) {
+    keep_pool_memory();
     void* p = nullptr;
     if (!check(cudaMallocAsync(&p, bytes, s), "cudaMallocAsync")) return nullptr;
     return p;
@@ -298,6 +316,29 @@ static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_
         configured.fetch_or(bit, std::memory_order_release);
     }
     run_kernel_dyn<KT><<<(unsigned)ctas, KT::NT, smem_bytes, s>>>(p);
+    return check(cudaGetLastError(), "kernel launch");
+}
+
+// kernels whose step count is run-time data (run_kernel_loop), run-time sized dynamic shared memory
+template <class KT>
+static bool launch_loop(const typename KT::Params& p, uint64_t ctas, uint32_t n_steps, size_t smem_bytes, size_t max_smem, stream_t s) {
+    if (ctas == 0) return true;
+    if (ctas > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        if (!check(cudaFuncSetAttribute(run_kernel_loop<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"))
+            return false;
+        cudaFuncSetAttribute(run_kernel_loop<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    run_kernel_loop<KT><<<(unsigned)ctas, KT::NT, smem_bytes, s>>>(p, n_steps);
     return check(cudaGetLastError(), "kernel launch");
 }
 

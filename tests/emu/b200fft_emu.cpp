@@ -96,6 +96,18 @@ static bool launch_dyn(const typename KT::Params& p, uint64_t ctas, size_t smem_
 }
 
 template <class KT>
+static bool launch_loop(const typename KT::Params& p, uint64_t ctas, uint32_t n_steps, size_t smem_bytes, size_t, stream_t) {
+    ++g_launches;
+    std::vector<cx<typename KT::T_>> smem(smem_bytes / sizeof(cx<typename KT::T_>) + 1);
+    for (uint64_t bid = 0; bid < ctas; ++bid) {
+        std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
+        for (uint32_t st = 0; st < n_steps; ++st)
+            for (int tid = 0; tid < KT::NT; ++tid) KT::step(p, (uint32_t)bid, tid, st, smem.data());
+    }
+    return true;
+}
+
+template <class KT>
 static int resident_ctas() { return 296; }  // what a B200 reports for a 2-CTA/SM kernel; only steers chunk sizes
 
 // persistent pipelined kernels: tiles in order; the TMA bulk copy of a tile becomes a memcpy

@@ -19,12 +19,14 @@ def dirty(n, dtype):
 
 
 def check_fft_algorithm(planner, n, direction, dtype, control_kind=oracle.CONTROL, chunks=3, seed=None,
-                        strict_factor=4.0):
+                        strict_factor=4.0, recipe=None):
     """All four entry points must agree with the oracle control under the reference's criterion
     (mean |a-b| < 0.1) AND the strict bounds of SURVEY.md 8(c): relative L2 vs the f64 truth
     <= 4 eps log2 N, and not worse than 2x the oracle's own error on the same input."""
     inverse = direction == rb.FftDirection.Inverse
-    fft = planner.plan_fft(n, direction)
+    # recipe: the caller owns planning (b200fft_plan_create_from_recipe) -- the way the reference's unit tests build one
+    # algorithm directly (e.g. RadersAlgorithm::new(inner), src/algorithm/raders_algorithm.rs:324-329)
+    fft = planner.plan_fft(n, direction) if recipe is None else planner.plan_fft_with_recipe(recipe, direction)
     assert fft.len() == n and fft.fft_direction() == direction
     x = signal(chunks * n, dtype, seed=n if seed is None else seed)
     want = oracle.fft(x, n, inverse, kind=control_kind)

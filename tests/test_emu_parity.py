@@ -6,6 +6,7 @@ import pytest
 
 import oracle
 import rustfft_b200 as rb
+import plan_kinds
 from protocol import check_error_behaviour, check_fft_algorithm, check_planner_cache
 from util import emu_library, rel_l2, signal, truth
 
@@ -126,11 +127,18 @@ def test_largest_four_step_f32(lib):
     assert f.describe().startswith("FourStep{1024x1024")
 
 
+@pytest.mark.parametrize("check", plan_kinds.ALL, ids=[c.__name__[6:] for c in plan_kinds.ALL])
+def test_round2_plan_kinds(planner, check):
+    """General Rader, MixedRadix{r0 x Rader}, Good-Thomas, Bluestein over smooth lengths, caller-owned recipes (tests/plan_kinds.py)."""
+    pl, dtype = planner
+    check(pl, dtype)
+
+
 @pytest.mark.parametrize("n,desc", [
     (65537, "Rader{n=65537,g=3,inner=FourStep{256x256}}"),          # BASELINE config 4
-    (2049, "Bluestein{n=2049,M=8192,inner=FourStep{64x128}}"),
+    (4099, "Bluestein{n=4099,M=16384,inner=FourStep{128x128}}"),
     (10007, "Bluestein{n=10007,M=32768,inner=FourStep{128x256}}"),
-    (112501, "Bluestein{n=112501,M=262144,inner=FourStep{512x512}}"),  # a 32-bit-overflow prime of raders_algorithm.rs:311-322
+    (216569, "Bluestein{n=216569,M=524288,inner=FourStep{512x1024}}"),  # a 32-bit-overflow prime of raders_algorithm.rs:311-322
 ])
 def test_large_convolution_plans(planner, n, desc):
     pl, dtype = planner

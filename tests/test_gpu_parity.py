@@ -13,6 +13,7 @@ import pytest
 
 import oracle
 import rustfft_b200 as rb
+import plan_kinds
 from protocol import check_error_behaviour, check_fft_algorithm, check_planner_cache
 from util import EPS, rel_l2, signal, strict_bound, truth
 
@@ -145,6 +146,13 @@ def test_large_non_power_of_two(planner, n):
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
 
 
+@pytest.mark.parametrize("check", plan_kinds.ALL, ids=[c.__name__[6:] for c in plan_kinds.ALL])
+def test_round2_plan_kinds(planner, check):
+    """General Rader, MixedRadix{r0 x Rader}, Good-Thomas, Bluestein over smooth lengths, caller-owned recipes (tests/plan_kinds.py)."""
+    pl, dtype = planner
+    check(pl, dtype)
+
+
 @pytest.mark.parametrize("n", [4225, 5000, 6000, 10000, 17017, 29791, 44100, 48000, 100000, 196608, 1000000])
 def test_smooth_composites_two_pass(planner, n):
     """Composite lengths above the one-pass limit, prime factors <= 31: SmoothFourStep (two passes, run-time radix
@@ -221,6 +229,25 @@ def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variant_check.py")], env=e, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sharded_scatter_fft_gather_two_gpus(torch_cuda):
+    """BASELINE config 5's data path on hardware: NCCL scatter of batch shards -> FFT per GPU -> gather, two ranks under torchrun
+    (skipped on a one-GPU box; tests/test_sharding_gloo.py covers the host logic on the CPU)."""
+    import os
+    import subprocess
+    import sys
+
+    from util import ROOT
+
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    e = dict(os.environ)
+    e["PYTHONPATH"] = ROOT + os.pathsep + os.path.join(ROOT, "tests")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(ROOT, "tests", "sharded_gpu_check.py")], env=e, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "SHARDED-OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_host_pipeline_many_chunks(torch_cuda):
