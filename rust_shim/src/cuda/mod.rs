@@ -24,10 +24,28 @@ pub struct B200FftPlan {
 extern "C" {
     pub fn b200fft_device_count(n: *mut c_int) -> c_int;
     pub fn b200fft_plan_create(out: *mut *mut B200FftPlan, len: u64, direction: c_int, precision: c_int, device: c_int) -> c_int;
+    pub fn b200fft_plan_create_from_recipe(out: *mut *mut B200FftPlan, nodes: *const B200FftRecipeNode, n_nodes: u32, direction: c_int,
+                                           precision: c_int, device: c_int) -> c_int;
     pub fn b200fft_plan_destroy(plan: *mut B200FftPlan) -> c_int;
     pub fn b200fft_exec_host_inplace(plan: *const B200FftPlan, buffer: *mut c_void, n_complex: u64) -> c_int;
     pub fn b200fft_exec_host_outofplace(plan: *const B200FftPlan, input: *const c_void, output: *mut c_void, n_complex: u64) -> c_int;
     pub fn b200fft_last_error() -> *const c_char;
+}
+
+/// `b200fft_recipe_node` of include/b200fft.h: the decomposition the Rust planner chose (`crate::plan::Recipe`,
+/// src/plan.rs:134-226), flattened -- node 0 is the root, `child` is the inner FFT of a Rader / Bluestein node.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct B200FftRecipeNode {
+    pub kind: u32, // 0 auto, 1 pow2, 2 smooth, 3 mixed radix, 4 good-thomas, 5 rader, 6 bluestein
+    pub child: u32,
+    pub len: u64,
+    pub a: u64,
+    pub b: u64,
+}
+
+pub(crate) fn last_error_text() -> String {
+    last_error()
 }
 
 fn last_error() -> String {
@@ -67,6 +85,25 @@ impl<T: FftNum> CudaFft<T> {
             return None;
         }
         Some(Self { plan, len, direction, _phantom: std::marker::PhantomData })
+    }
+}
+
+impl<T: FftNum> CudaFft<T> {
+    /// Planning owned by Rust (north_star: "Rust host code owns planning ... and calls through a thin extern C FFI"): the
+    /// recipe `FftPlannerScalar::design_fft_for_len` produced, handed over as data.  `None` when the library has no kernel
+    /// sequence for that decomposition -- the caller then retries with `CudaFft::new` (the library's own choice).
+    pub fn from_recipe(nodes: &[B200FftRecipeNode], direction: FftDirection, device: i32) -> Option<Self> {
+        let precision = if TypeId::of::<T>() == TypeId::of::<f32>() { 0 } else if TypeId::of::<T>() == TypeId::of::<f64>() { 1 } else { return None };
+        let dir = match direction {
+            FftDirection::Forward => 0,
+            FftDirection::Inverse => 1,
+        };
+        let mut plan: *mut B200FftPlan = std::ptr::null_mut();
+        let rc = unsafe { b200fft_plan_create_from_recipe(&mut plan, nodes.as_ptr(), nodes.len() as u32, dir, precision, device) };
+        if rc != 0 {
+            return None;
+        }
+        Some(Self { plan, len: nodes[0].len as usize, direction, _phantom: std::marker::PhantomData })
     }
 }
 

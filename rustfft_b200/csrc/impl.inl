@@ -140,6 +140,19 @@ B2_FUSED(2048, 4, 2, 32, 32)
 B2_FUSED(4096, 2, 4, 32, 32)
 static constexpr int FUSED_NG = 2, FUSED_NS = 3;  // consumer groups, shared-memory stages
 
+// compiled tiles of COMPOSITE pass lengths (f32): the same CTA engine with radix-3 / 5 / 7 stages, for the two-pass plans of
+// 10000 = 100 x 100, 44100 = 196 x 225, 48000 = 128 x 375, 100000 = 100 x 1000 and 10^6 = 1000 x 1000 (the run-time-radix
+// SmoothPassKernel is instruction bound at ~0.12 of the roofline; every radix must divide the E elements a thread holds)
+template <int L> struct SmoothTileGeo;
+template <> struct SmoothTileGeo<100> { using type = Geo<float, 100, 20, 32, Radices<4, 5, 5>>; };
+template <> struct SmoothTileGeo<128> { using type = Geo<float, 128, 16, 16, Radices<8, 16>>; };
+template <> struct SmoothTileGeo<196> { using type = Geo<float, 196, 28, 16, Radices<4, 7, 7>>; };
+template <> struct SmoothTileGeo<225> { using type = Geo<float, 225, 15, 16, Radices<3, 3, 5, 5>>; };
+template <> struct SmoothTileGeo<375> { using type = Geo<float, 375, 15, 16, Radices<3, 5, 5, 5>>; };
+template <> struct SmoothTileGeo<1000> { using type = Geo<float, 1000, 40, 8, Radices<8, 5, 5, 5>>; };
+struct CompiledPair { uint32_t a, b; };
+static constexpr CompiledPair COMPILED_PAIRS[] = {{100, 100}, {196, 225}, {128, 375}, {100, 1000}, {1000, 1000}};
+
 // largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
 template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
 static constexpr size_t MAX_SMEM_PER_CTA = 227 * 1024;  // opt-in dynamic shared memory limit of sm_100
@@ -1454,6 +1467,122 @@ struct Builder {
         return true;
     }
 
+    // ---------------- compiled two-pass plans of composite lengths (f32; SmoothTileGeo) ----------------
+    // B200FFT_SMOOTH_COMPILED=0: the run-time-radix passes for these lengths too (A/B measurements)
+    static bool use_compiled_smooth() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_SMOOTH_COMPILED");
+            return !(e && std::atoi(e) == 0);
+        }();
+        return v;
+    }
+    static bool compiled_pair(uint64_t n, uint32_t& a, uint32_t& b) {
+        if (sizeof(T) != 4 || !use_compiled_smooth()) return false;
+        for (const CompiledPair& cp : COMPILED_PAIRS)
+            if ((uint64_t)cp.a * cp.b == n) {
+                a = cp.a;
+                b = cp.b;
+                return true;
+            }
+        return false;
+    }
+    // chunks of a multi-pass plan rotate over up to K streams (the caller's + auxiliary ones, fork / join with events); body(b0, nb, k,
+    // stream) issues the launches of one chunk, k = which workspace
+    template <class Body>
+    static bool run_chunks(b200fft_plan* self, const ExecCtx& c, uint64_t chunk, int K, Body body) {
+        const uint64_t nchunks = (c.batch + chunk - 1) / chunk;
+        const int ns = (int)std::min<uint64_t>((uint64_t)(c.max_streams > 0 ? std::min(c.max_streams, K) : K), nchunks);
+        rt::stream_t st[4] = {c.stream, nullptr, nullptr, nullptr};
+        rt::event_t ev_fork = nullptr;
+        if (ns > 1) {
+            ev_fork = rt::event_create();
+            if (!ev_fork || !rt::event_record(ev_fork, c.stream)) return false;
+            for (int k = 1; k < ns; ++k) {
+                st[k] = self->aux_get();
+                if (!st[k] || !rt::stream_wait(st[k], ev_fork)) return false;
+            }
+        }
+        bool ok = true;
+        uint64_t idx = 0;
+        for (uint64_t b0 = 0; b0 < c.batch && ok; b0 += chunk, ++idx) {
+            const int k = (int)(idx % (uint64_t)ns);
+            ok = body(b0, std::min(chunk, c.batch - b0), k, st[k]);
+        }
+        if (ns > 1) {
+            for (int k = 1; k < ns; ++k) {
+                rt::event_t ev = rt::event_create();
+                ok = ev && rt::event_record(ev, st[k]) && rt::stream_wait(c.stream, ev) && ok;
+                if (ev) rt::event_destroy(ev);
+                self->aux_put(st[k]);
+            }
+            rt::event_destroy(ev_fork);
+        }
+        return ok;
+    }
+    template <int L1, int L2, bool SW>
+    static bool make_compiled_smooth_t(b200fft_plan& pl) {
+        if constexpr (sizeof(T) == 4) {
+            using GA = typename SmoothTileGeo<L1>::type;
+            using GB = typename SmoothTileGeo<L2>::type;
+            using KA = FftKernel<GA, FF, FF, LoadColsG<T, SW>, StoreColsG<T>>;
+            using KB = FftKernel<GB, JF, FF, LoadRowsTwG<T>, StoreTransposedG<T, SW>>;
+            const uint64_t N = (uint64_t)L1 * L2;
+            const C* twa = upload(pl, stage_twiddles<GA>());
+            const C* twb = upload(pl, stage_twiddles<GB>());
+            const C* full_tw = smooth_full_twiddles(pl, L1, L2);
+            if (!twa || !twb || !full_tw) return false;
+            const int K = overlap_streams(4);
+            // K chunks in flight share ~48 MiB of L2; FFT indices of a launch stay below 2^31
+            uint64_t chunk = std::max<uint64_t>(1, (48ull << 20) / (N * sizeof(C)) / (uint64_t)K);
+            chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(L1, L2));
+            pl.chunk = chunk;
+            pl.work_bytes = [=](uint64_t batch) {
+                const uint64_t nchunks = (batch + chunk - 1) / chunk;
+                return std::min(batch, chunk) * N * sizeof(C) * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
+            };
+            pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+            b200fft_plan* self = &pl;
+            const FastDiv d1 = make_fastdiv(L1), d2 = make_fastdiv(L2);
+            pl.exec = [=](const ExecCtx& c) {
+                const C* in = (const C*)c.in;
+                C* out = (C*)c.out;
+                C* work = (C*)c.work;
+                return run_chunks(self, c, chunk, K, [&](uint64_t b0, uint64_t nb, int k, rt::stream_t s) {
+                    C* w = work + (uint64_t)k * chunk * N;
+                    typename KA::Params a;
+                    a.load = LoadColsG<T, SW>{in + b0 * N, N, (uint32_t)L2, d2};
+                    a.store = StoreColsG<T>{w, N, (uint32_t)L2, d2};
+                    a.tw = twa;
+                    a.n_fft = nb * L2;
+                    if (!rt::launch<KA>(a, (a.n_fft + GA::F - 1) / GA::F, s)) return false;
+                    typename KB::Params b;
+                    b.load = LoadRowsTwG<T>{w, full_tw, (uint32_t)L2, (uint32_t)L1, d1, use_discard() ? 1u : 0u};
+                    b.store = StoreTransposedG<T, SW>{out + b0 * N, N, (uint32_t)L1, d1};
+                    b.tw = twb;
+                    b.n_fft = nb * L1;
+                    return rt::launch<KB>(b, (b.n_fft + GB::F - 1) / GB::F, s);
+                });
+            };
+            pl.desc = "SmoothFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",compiled}";
+            return true;
+        } else {
+            (void)pl;
+            return false;
+        }
+    }
+    static bool make_compiled_smooth(b200fft_plan& pl, uint32_t a, uint32_t b) {
+        const bool sw = pl.direction != 0;
+#define B2_CPAIR(A, B) \
+    if (a == A && b == B) return sw ? make_compiled_smooth_t<A, B, true>(pl) : make_compiled_smooth_t<A, B, false>(pl);
+        B2_CPAIR(100, 100)
+        B2_CPAIR(196, 225)
+        B2_CPAIR(128, 375)
+        B2_CPAIR(100, 1000)
+        B2_CPAIR(1000, 1000)
+#undef B2_CPAIR
+        return false;
+    }
+
     // ---------------- SmoothConv: Rader / Bluestein in ONE CTA pass over a smooth inner length (kernels.h) ----------------
     static constexpr uint32_t CONV_SMOOTH_MAX = sizeof(T) == 4 ? 6144 : 3072;  // 2 M sizeof(C) <= 96 KiB: two CTAs per SM
     static std::string radix_string(const std::vector<uint32_t>& r) {
@@ -1783,6 +1912,13 @@ struct Builder {
     }
     // B200FFT_BLUESTEIN_SMOOTH_BIG=1: also above the one-pass limit (four run-time-radix passes over the smooth length instead of
     // four compiled passes over the next power of two); otherwise reachable through a recipe only
+    static bool rader_smooth_big() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_RADER_SMOOTH_BIG");
+            return e && std::atoi(e) == 1;
+        }();
+        return v;
+    }
     static bool bluestein_smooth_big() {
         static bool v = [] {
             const char* e = std::getenv("B200FFT_BLUESTEIN_SMOOTH_BIG");
@@ -1793,7 +1929,7 @@ struct Builder {
     static uint64_t bluestein_smooth_pct() {
         static uint64_t v = [] {
             const char* e = std::getenv("B200FFT_BLUESTEIN_SMOOTH");
-            return e ? (uint64_t)std::atoi(e) : (uint64_t)70;
+            return e ? (uint64_t)std::atoi(e) : (uint64_t)0;  // measured: the smooth inner FFT loses to the next power of two at every ratio tried
         }();
         return v;
     }
@@ -1834,6 +1970,10 @@ struct Builder {
                     break;
                 }
                 if (b > SMOOTH_MAX || !smooth_factor_any(a) || !smooth_factor_any(b)) return unsupported("both factors must be smooth one-pass lengths");
+                if (uint32_t c1 = 0, c2 = 0; r.kind == B200FFT_RECIPE_MIXED_RADIX && compiled_pair(n, c1, c2) && c1 == a && c2 == b) {
+                    ok = make_compiled_smooth(pl, c1, c2);
+                    break;
+                }
                 ok = smooth_dispatch(pl, r.kind == B200FFT_RECIPE_GOOD_THOMAS ? 4 : 1, (uint32_t)a, (uint32_t)b);
                 break;
             }
@@ -1924,6 +2064,8 @@ struct Builder {
                 return fail(B200FFT_ERR_UNSUPPORTED, "power-of-two lengths above 2^24 are not planned by this build");
         } else if (std::vector<uint32_t> radices; n <= SMOOTH_MAX && smooth_factor(n, radices)) {
             ok = smooth_dispatch(pl, 0, 0, 0);  // every prime factor <= 31
+        } else if (uint32_t c1 = 0, c2 = 0; n > SMOOTH_MAX && compiled_pair(n, c1, c2)) {
+            ok = make_compiled_smooth(pl, c1, c2);  // two passes through compiled composite tiles
         } else if (uint32_t g1 = 0, g2 = 0; use_good_thomas() && n > SMOOTH_MAX && coprime_split(n, g1, g2)) {
             ok = smooth_dispatch(pl, 4, g1, g2);  // opt-in (B200FFT_GOOD_THOMAS=1): coprime split, no inter-pass twiddles
         } else if (uint32_t s1 = 0, s2 = 0; n > SMOOTH_MAX && n <= (1ull << 23) && smooth_split(n, s1, s2)) {
@@ -1938,9 +2080,15 @@ struct Builder {
             const uint64_t p = hm::largest_prime_factor(n), r0 = n / p;
             std::vector<uint32_t> rr;
             uint32_t b1 = 0, b2 = 0;
-            if (use_general_rader() && r0 <= 8 && r0 * (p - 1) <= CONV_SMOOTH_MAX && smooth_factor(p - 1, rr)) {
+            // Measured on B200 (profiles/r2d_ab_plans.txt): the one-pass Rader over a smooth p - 1 beats the fused Bluestein it replaces
+            // by 1.1-1.8x in f64 at every size and in f32 from the point where Bluestein needs M >= 2048 (617: 1.7x, 2053: 1.3x, 1009 and
+            // 1234: a tie); below that the compiled power-of-two Bluestein kernels win (37, 97: 0.75x) and keep the length.  Above
+            // the one-pass limit Rader runs four run-time-radix passes, ~2x SLOWER than Bluestein's four compiled power-of-two passes
+            // over 2-4x the data (7681, 112501): recipe / B200FFT_RADER_SMOOTH_BIG=1 only.
+            const bool rader_one_pass_wins = sizeof(T) == 8 || hm::next_pow2(2 * n - 1) >= 2048;
+            if (use_general_rader() && rader_one_pass_wins && r0 <= 8 && r0 * (p - 1) <= CONV_SMOOTH_MAX && smooth_factor(p - 1, rr)) {
                 ok = smooth_dispatch(pl, 2, (uint32_t)r0, (uint32_t)p);  // one CTA pass: MixedRadix{r0 x Rader(p)} fused
-            } else if (use_general_rader() && r0 == 1 && smooth_factor_any(p - 1) && smooth_split(p - 1, b1, b2)) {
+            } else if (use_general_rader() && rader_smooth_big() && r0 == 1 && smooth_factor_any(p - 1) && smooth_split(p - 1, b1, b2)) {
                 ok = smooth_dispatch(pl, 5, b1, b2);  // easy prime above the one-pass limit: four passes over n - 1
             } else {
                 const uint64_t M2 = hm::next_pow2(2 * n - 1);

@@ -27,9 +27,39 @@ namespace b2 {
 // resident CTAs per SM the register allocator must leave room for: 64 registers per thread for the
 // 16-element geometries (2048 threads per SM), 128 for the 32-element (radix-32) ones
 constexpr int default_min_blocks(int nt, int e = 16) {
-    const int target_threads = e >= 32 ? 512 : 1024;
+    const int target_threads = e >= 24 ? 512 : 1024;
     const int b = target_threads / nt;
     return b < 1 ? 1 : (b > 8 ? 8 : b);
+}
+
+// unsigned division by a run-time constant through a precomputed reciprocal (the stage geometry of the
+// SmoothKernel is run-time data; plain `/` and `%` cost ~20 instructions each)
+struct FastDiv {
+    uint32_t d, mul, shift;  // q = umulhi(n, mul) >> shift   (n < 2^31)
+    B2_HD uint32_t div(uint32_t n) const {
+        if (d == 1) return n;
+#if defined(__CUDA_ARCH__)
+        return __umulhi(n, mul) >> shift;
+#else
+        return (uint32_t)(((uint64_t)n * mul) >> 32) >> shift;
+#endif
+    }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d, 0, 0};
+    if (d <= 1) return f;
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;  // ceil(log2 d)
+    // round-up method, exact for n < 2^31
+    const uint64_t m = ((1ull << (32 + l)) + d - 1) / d;
+    if (m < (1ull << 32)) {
+        f.mul = (uint32_t)m;
+        f.shift = l;
+    } else {  // m needs 33 bits: use l-1 (still exact for n < 2^31 because d > 2^(l-1))
+        f.mul = (uint32_t)(((1ull << (32 + l - 1)) + d - 1) / d);
+        f.shift = l - 1;
+    }
+    return f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -141,6 +171,83 @@ struct StoreTransposed {
     }
     B2_HD void put(const St& s, int e, cx<T> v) const {
         if (s.ok) st_cs(s.p + ((uint32_t)e << lg1), SWAP ? swap_ri(v) : v);
+    }
+};
+
+// ---- the same four functors for ARBITRARY N1, N2 (compiled two-pass plans of composite lengths: 10000 = 100 x 100,
+// 44100 = 196 x 225, 48000 = 128 x 375, 10^6 = 1000 x 1000): shifts become multiplications, g -> (transform, column | row)
+// goes through a precomputed reciprocal.  The reference's MixedRadix for the same sizes: src/algorithm/mixed_radix.rs:128-158.
+template <typename T, bool SWAP>
+struct LoadColsG {  // pass A: FFT g = (b, c), g = b*N2 + c; element e at in[b*N + e*N2 + c]
+    const cx<T>* in;
+    uint64_t N;
+    uint32_t N2;
+    FastDiv div2;
+    struct St { const cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint32_t b = div2.div((uint32_t)g), c = (uint32_t)g - b * N2;
+        return St{in + (uint64_t)b * N + c, ok};
+    }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        cx<T> v = ld_cs(s.p + (size_t)e * N2);
+        return SWAP ? swap_ri(v) : v;
+    }
+};
+template <typename T>
+struct StoreColsG {  // pass A: out[b*N + k1*N2 + c] (the slots the tile was read from)
+    cx<T>* out;
+    uint64_t N;
+    uint32_t N2;
+    FastDiv div2;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint32_t b = div2.div((uint32_t)g), c = (uint32_t)g - b * N2;
+        return St{out + (uint64_t)b * N + c, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) s.p[(size_t)e * N2] = v;  // plain write-back store: pass B re-reads it from L2
+    }
+};
+template <typename T>
+struct LoadRowsTwG {  // pass B: row k1 of transform b (g = b*N1 + k1), element n2 = e, times W_N^(k1 n2) from the [k1][n2] table
+    const cx<T>* in;
+    const cx<T>* tw;
+    uint32_t len;  // N2
+    uint32_t N1;
+    FastDiv div1;
+    uint32_t discard = 0;
+    B2_HD void tile_done(uint64_t g0, uint32_t n_ffts, int tid, int nt) const {
+        if (!discard) return;
+        const uint64_t bytes = (uint64_t)n_ffts * len * sizeof(cx<T>), off = g0 * (uint64_t)len * sizeof(cx<T>);
+        if ((bytes | off) & 127u) return;  // whole, aligned 128-byte lines only
+        const char* base = reinterpret_cast<const char*>(in) + off;
+        for (uint32_t l = (uint32_t)tid; l < (uint32_t)(bytes / 128); l += (uint32_t)nt) l2_discard_line(base + (size_t)l * 128);
+    }
+    static constexpr bool HAS_TILE_DONE = true;
+    struct St { const cx<T>* p; const cx<T>* t; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint32_t b = div1.div((uint32_t)g), k1 = (uint32_t)g - b * N1;
+        return St{in + g * (uint64_t)len, tw + (uint64_t)k1 * len, ok};
+    }
+    B2_HD cx<T> get(const St& s, int e) const {
+        if (!s.ok) return mk<T>(0, 0);
+        return cmul(ld_cs(s.p + e), ldg_stream(s.t + e));
+    }
+};
+template <typename T, bool SWAP>
+struct StoreTransposedG {  // pass B: output k2 = e of row k1 goes to out[b*N + k1 + N1*e]
+    cx<T>* out;
+    uint64_t N;
+    uint32_t N1;
+    FastDiv div1;
+    struct St { cx<T>* p; bool ok; };
+    B2_HD St prep(uint64_t g, bool ok) const {
+        const uint32_t b = div1.div((uint32_t)g), k1 = (uint32_t)g - b * N1;
+        return St{out + (uint64_t)b * N + k1, ok};
+    }
+    B2_HD void put(const St& s, int e, cx<T> v) const {
+        if (s.ok) st_cs(s.p + (size_t)e * N1, SWAP ? swap_ri(v) : v);
     }
 };
 
@@ -520,36 +627,6 @@ struct RaderKernel {
 // power-of-two geometries (no cross-stage register reuse, generic index arithmetic) but one pass over
 // HBM and no padding to a power of two -- against Bluestein's two FFTs of 2-4x the length.
 // ------------------------------------------------------------------------------------------
-// unsigned division by a run-time constant through a precomputed reciprocal (the stage geometry of the
-// SmoothKernel is run-time data; plain `/` and `%` cost ~20 instructions each)
-struct FastDiv {
-    uint32_t d, mul, shift;  // q = umulhi(n, mul) >> shift   (n < 2^31)
-    B2_HD uint32_t div(uint32_t n) const {
-        if (d == 1) return n;
-#if defined(__CUDA_ARCH__)
-        return __umulhi(n, mul) >> shift;
-#else
-        return (uint32_t)(((uint64_t)n * mul) >> 32) >> shift;
-#endif
-    }
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f{d, 0, 0};
-    if (d <= 1) return f;
-    uint32_t l = 0;
-    while ((1u << l) < d) ++l;  // ceil(log2 d)
-    // round-up method, exact for n < 2^31
-    const uint64_t m = ((1ull << (32 + l)) + d - 1) / d;
-    if (m < (1ull << 32)) {
-        f.mul = (uint32_t)m;
-        f.shift = l;
-    } else {  // m needs 33 bits: use l-1 (still exact for n < 2^31 because d > 2^(l-1))
-        f.mul = (uint32_t)(((1ull << (32 + l - 1)) + d - 1) / d);
-        f.shift = l - 1;
-    }
-    return f;
-}
-
 template <typename T, bool SWAP>
 struct SmoothKernel {
     using T_ = T;

@@ -45,35 +45,49 @@ def check_rader_primes_below_100(planner, dtype):
 
 
 def check_default_prime_rule(planner, dtype):
-    """src/plan.rs:636-664: Rader when p - 1 factors into small primes, Bluestein otherwise (describe() shows the choice)."""
+    """src/plan.rs:636-664: Rader when p - 1 factors into small primes, Bluestein otherwise -- re-decided by measurement on the B200
+    (profiles/r2d_ab_plans.txt): the one-pass Rader is the default in f64 and, in f32, from the size where Bluestein needs M >= 2048;
+    above the one-pass limit the four run-time-radix passes lose to Bluestein over a power of two and stay recipe-only."""
     f32 = dtype == np.complex64
     cases = [(617, "Rader{n=617,g=3,inner=Smooth{616=11x7x8},fused}"), (719, "Bluestein{"), (2053, "Rader{n=2053,g=2,inner=Smooth{2052=19x3x3x3x4},fused}"),
              (1009, "Rader{n=1009,g=11,inner=Smooth{1008=7x3x3x16},fused}"), (257, "Rader{n=257,g=3,fused}"),
-             (4051, "Rader{n=4051,g=10,inner=Smooth{4050=5x5x3x3x3x3x2},fused}" if f32 else "Rader{n=4051,g=10,inner=SmoothFourStep{54x75}}"),
-             (7681, "Rader{n=7681,g=17,inner=SmoothFourStep{80x96}}")]
+             (97, "Bluestein{n=97,M=256,fused}" if f32 else "Rader{n=97,g=5,inner=Smooth{96=3x16x2},fused}"),
+             (4051, "Rader{n=4051,g=10,inner=Smooth{4050=5x5x3x3x3x3x2},fused}" if f32 else "Bluestein{n=4051,M=8192,inner=FourStep{64x128}}"),
+             (7681, "Bluestein{n=7681,M=16384,inner=FourStep{128x128}}")]
     for n, want in cases:
         f = check_fft_algorithm(planner, n, DIRS[n % 2], dtype, control_kind=oracle.PLANNER, chunks=40 if n < 3000 else 3)
         assert f.describe().startswith(want), (n, f.describe())
+    for n, want in [(4051, "Rader{n=4051,g=10,inner=SmoothFourStep{54x75}}" if not f32 else None), (7681, "Rader{n=7681,g=17,inner=SmoothFourStep{80x96}}")]:
+        if want:
+            f = check_fft_algorithm(planner, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=3, recipe=R.rader(n))
+            assert f.describe() == want, f.describe()
 
 
 def check_mixed_radix_rader(planner, dtype):
     """len = r0 x p, p an easy prime: the reference's MixedRadix{r0, Rader(p)} (1234 = 2 x 617 is BASELINE config 3's plan),
-    here one CTA pass.  More virtual transforms than one CTA holds, ragged last CTA."""
-    for n, want in [(1234, "MixedRadix{2xRader{n=617,g=3,inner=Smooth{616=11x7x8},fused},fused}"), (94, "MixedRadix{2xRader{n=47,"),
-                    (188, "MixedRadix{4xRader{n=47,"), (296, "MixedRadix{8xRader{n=37,"), (606, "MixedRadix{6xRader{n=101,"),
-                    (2049, "MixedRadix{3xRader{n=683,"), (335, "MixedRadix{5xRader{n=67,"), (7 * 103, "MixedRadix{7xRader{n=103,")]:
+    here one CTA pass.  More virtual transforms than one CTA holds, ragged last CTA.  (Small lengths are planned as Bluestein by default
+    in f32 -- measured faster -- so every case is also built from its recipe.)"""
+    for n, r0, want in [(1234, 2, "MixedRadix{2xRader{n=617,g=3,inner=Smooth{616=11x7x8},fused},fused}"), (94, 2, "MixedRadix{2xRader{n=47,"),
+                        (188, 4, "MixedRadix{4xRader{n=47,"), (296, 8, "MixedRadix{8xRader{n=37,"), (606, 6, "MixedRadix{6xRader{n=101,"),
+                        (2049, 3, "MixedRadix{3xRader{n=683,"), (335, 5, "MixedRadix{5xRader{n=67,"), (7 * 103, 7, "MixedRadix{7xRader{n=103,")]:
         for d in DIRS:
-            f = check_fft_algorithm(planner, n, d, dtype, control_kind=oracle.PLANNER, chunks=37 if d == DIRS[0] else 2)
+            f = check_fft_algorithm(planner, n, d, dtype, control_kind=oracle.PLANNER, chunks=37 if d == DIRS[0] else 2, recipe=R.rader(n, r0))
             assert f.describe().startswith(want), (n, f.describe())
+    f = check_fft_algorithm(planner, 1234, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=5)  # the default plan of config 3's length
+    assert f.describe().startswith("MixedRadix{2xRader{n=617,"), f.describe()
 
 
 def check_overflow_primes(planner, dtype):
     """raders_algorithm.rs:311-322: 112501 (112500 = 2^2 3^2 5^5: Rader over a two-pass smooth inner FFT), 216569 and 417623
     (p - 1 has a factor above 31: Bluestein); index products exceed 32 bits in all three."""
-    for n, want in [(112501, "Rader{n=112501,g=10,inner=SmoothFourStep{300x375}}"), (216569, "Bluestein{n=216569"), (417623, "Bluestein{n=417623")]:
+    for n in (112501, 216569, 417623):  # default: Bluestein over a power of two (measured faster than Rader's four run-time-radix passes)
         f = check_fft_algorithm(planner, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2)
-        assert f.describe().startswith(want), f.describe()
-    check_fft_algorithm(planner, 112501, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=1)
+        assert f.describe().startswith("Bluestein{n=%d," % n), f.describe()
+    for d in DIRS:  # RadersAlgorithm::new(inner) for the first of them, as the reference's test builds it
+        f = check_fft_algorithm(planner, 112501, d, dtype, control_kind=oracle.PLANNER, chunks=2, recipe=R.rader(112501))
+        assert f.describe() == "Rader{n=112501,g=10,inner=SmoothFourStep{300x375}}", f.describe()
+    with pytest.raises(rb.FftError, match="RADER"):
+        planner.plan_fft_with_recipe(R.rader(216569), DIRS[0])
 
 
 def check_good_thomas_small_pairs(planner, dtype):
@@ -111,13 +125,16 @@ def check_bluestein_inner_lengths(planner, dtype):
         for d in DIRS:
             f = check_fft_algorithm(planner, rc.len, d, dtype, control_kind=oracle.PLANNER, recipe=rc, chunks=3)
             assert f.describe() == want, f.describe()
-    f = check_fft_algorithm(planner, 1283, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=9)  # default rule picks the smooth length
-    assert f.describe() == "Bluestein{n=1283,M=2592,inner=Smooth{2592=3x3x3x3x16x2},fused}"
+    f = check_fft_algorithm(planner, 1283, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=9)  # default: the next power of two (measured faster)
+    assert f.describe() == "Bluestein{n=1283,M=4096,fused}"
+    for d in DIRS:
+        f = check_fft_algorithm(planner, 1283, d, dtype, control_kind=oracle.PLANNER, chunks=9, recipe=R.bluestein(1283, R.smooth(2592)))
+        assert f.describe() == "Bluestein{n=1283,M=2592,inner=Smooth{2592=3x3x3x3x16x2},fused}"
 
 
 def check_recipes_of_existing_kinds(planner, dtype):
     for rc, want in [(R.pow2(1024), "Direct{1024}"), (R.pow2(1 << 15), "FourStep{128x256"), (R.mixed_radix(128, 256), "FourStep{128x256"),
-                     (R.smooth(1000), "Smooth{1000=5x5x5x8}"), (R.mixed_radix(100, 100), "SmoothFourStep{100x100}"),
+                     (R.smooth(1000), "Smooth{1000=5x5x5x8}"), (R.mixed_radix(100, 100), "SmoothFourStep{100x100"), (R.mixed_radix(50, 100), "SmoothFourStep{50x100}"),
                      (R.rader(257), "Rader{n=257,g=3,fused}"), (R.rader(65537, 1, R.pow2(65536)), "Rader{n=65537,g=3,inner=FourStep{256x256}}"),
                      (R.bluestein(37), "Bluestein{n=37,M=128,fused}")]:
         f = check_fft_algorithm(planner, rc.len, DIRS[0], dtype, control_kind=oracle.PLANNER, recipe=rc, chunks=2)

@@ -61,8 +61,26 @@ def test_smooth_four_step_plans(planner, n, desc):
     src/algorithm/mixed_radix.rs:128-158) instead of Bluestein's four."""
     pl, dtype = planner
     f = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=3)
-    assert f.describe() == desc
+    # f32: 10000 and 44100 run through compiled composite tiles (SmoothTileGeo: 100 x 100, 196 x 225)
+    compiled = {10000: "SmoothFourStep{100x100,compiled}", 44100: "SmoothFourStep{196x225,compiled}"}
+    assert f.describe() == (compiled.get(n, desc) if dtype == np.complex64 else desc)
     check_fft_algorithm(pl, n, DIRS[1], dtype, control_kind=oracle.PLANNER, chunks=2)
+    if dtype == np.complex64 and n in compiled:  # the run-time-radix passes of the same split stay reachable (other kernels)
+        a, b = (int(v) for v in desc[desc.index("{") + 1:-1].split("x"))
+        if (a, b) != tuple(int(v) for v in compiled[n][compiled[n].index("{") + 1:compiled[n].index(",")].split("x")):
+            g = check_fft_algorithm(pl, n, DIRS[0], dtype, control_kind=oracle.PLANNER, chunks=2, recipe=rb.Recipe.mixed_radix(a, b))
+            assert g.describe() == desc
+
+
+@pytest.mark.parametrize("n,batch,desc", [(10000, 70, "SmoothFourStep{100x100,compiled}"), (48000, 9, "SmoothFourStep{128x375,compiled}"),
+                                          (100000, 5, "SmoothFourStep{100x1000,compiled}"), (1000000, 2, "SmoothFourStep{1000x1000,compiled}")])
+def test_compiled_composite_two_pass_plans(lib, n, batch, desc):
+    """f32 two-pass plans whose pass lengths have compiled composite tiles (radix-3/5/7 stages in the CTA engine): ragged tiles
+    that straddle transforms, several chunks over several streams, both directions, all entry points."""
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    for d in DIRS:
+        f = check_fft_algorithm(pl, n, d, np.complex64, control_kind=oracle.PLANNER, chunks=batch if d == DIRS[0] else 1)
+        assert f.describe() == desc
 
 
 def test_random_smooth_composites(planner):
@@ -92,6 +110,8 @@ def test_smooth_four_step_chunks_and_large(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 100000, 45  # 32 MiB of intermediate = 41 transforms per chunk: two chunks, the second ragged
     f = pl.plan_fft_forward(n)
+    assert f.describe() == "SmoothFourStep{100x1000,compiled}"
+    f = pl.plan_fft_with_recipe(rb.Recipe.mixed_radix(250, 400), DIRS[0])
     assert f.describe() == "SmoothFourStep{250x400}" and f.launches(batch) == 4
     x = signal(n * batch, np.complex64, seed=3)
     y = x.copy()
@@ -99,7 +119,7 @@ def test_smooth_four_step_chunks_and_large(lib):
     for b in (0, 40, 41, 44):
         assert rel_l2(y[b * n:(b + 1) * n], truth(x[b * n:(b + 1) * n], n, False)) < 4 * 5.96e-8 * np.log2(n)
     f = pl.plan_fft_inverse(1000000)
-    assert f.describe() == "SmoothFourStep{1000x1000}"
+    assert f.describe() == "SmoothFourStep{1000x1000,compiled}"
     x = signal(1000000, np.complex64, seed=4)
     y = x.copy()
     f.process(y)
