@@ -83,7 +83,9 @@ int b200fft_plan_destroy(b200fft_plan* plan);
  *   GOOD_THOMAS   GoodThomasAlgorithm(+Small)           len = a * b, gcd(a, b) = 1, two passes without twiddles
  *   RADER         RadersAlgorithm                       len = a * p (a = 0 or 1: len = p prime; a in 2..8: MixedRadix{a x Rader(p)}
  *                                                       fused); child = node of the inner FFT of length p - 1 (0 = AUTO)
- *   BLUESTEIN     BluesteinsAlgorithm                   child = node of the inner FFT, length M >= 2 len - 1 (0 = AUTO) */
+ *   BLUESTEIN     BluesteinsAlgorithm                   child = node of the inner FFT, length M >= 2 len - 1 (0 = AUTO)
+ *   CLUSTER       MixedRadix, on chip                   len = 2^14 .. 2^17 (f32): both passes inside one thread-block cluster, the
+ *                                                       transpose through distributed shared memory (one pass over HBM) */
 enum {
     B200FFT_RECIPE_AUTO = 0,
     B200FFT_RECIPE_POW2 = 1,
@@ -91,7 +93,8 @@ enum {
     B200FFT_RECIPE_MIXED_RADIX = 3,
     B200FFT_RECIPE_GOOD_THOMAS = 4,
     B200FFT_RECIPE_RADER = 5,
-    B200FFT_RECIPE_BLUESTEIN = 6
+    B200FFT_RECIPE_BLUESTEIN = 6,
+    B200FFT_RECIPE_CLUSTER = 7
 };
 typedef struct b200fft_recipe_node {
     uint32_t kind;  /* B200FFT_RECIPE_* */

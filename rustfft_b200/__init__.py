@@ -60,7 +60,7 @@ class Recipe:
 
     Built with the class methods; `inner` is the Recipe of the inner FFT of a Rader / Bluestein node."""
 
-    AUTO, POW2, SMOOTH, MIXED_RADIX, GOOD_THOMAS, RADER, BLUESTEIN = range(7)
+    AUTO, POW2, SMOOTH, MIXED_RADIX, GOOD_THOMAS, RADER, BLUESTEIN, CLUSTER = range(8)
 
     def __init__(self, kind: int, len: int, a: int = 0, b: int = 0, inner: Optional["Recipe"] = None):
         self.kind, self.len, self.a, self.b, self.inner = kind, int(len), int(a), int(b), inner
@@ -68,6 +68,10 @@ class Recipe:
     @classmethod
     def pow2(cls, n):
         return cls(cls.POW2, n)
+
+    @classmethod
+    def cluster(cls, n):
+        return cls(cls.CLUSTER, n)
 
     @classmethod
     def smooth(cls, n):

@@ -25,6 +25,7 @@
 #include "../../include/b200fft.h"
 #include "host_math.h"
 #include "fused.h"
+#include "cluster.h"
 
 namespace b2 {
 
@@ -38,8 +39,9 @@ inline int fail(int code, const std::string& msg) {
 // which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
 // harness defines none and gets everything)
 #if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64) && \
-    !defined(B2_PART_FUSED32)
+    !defined(B2_PART_FUSED32) && !defined(B2_PART_CTILE32)
 #define B2_PART_FUSED32 1
+#define B2_PART_CTILE32 1
 #define B2_PART_CABI 1
 #define B2_PART_F32 1
 #define B2_PART_F64 1
@@ -144,14 +146,25 @@ static constexpr int FUSED_NG = 2, FUSED_NS = 3;  // consumer groups, shared-mem
 // 10000 = 100 x 100, 44100 = 196 x 225, 48000 = 128 x 375, 100000 = 100 x 1000 and 10^6 = 1000 x 1000 (the run-time-radix
 // SmoothPassKernel is instruction bound at ~0.12 of the roofline; every radix must divide the E elements a thread holds)
 template <int L> struct SmoothTileGeo;
+template <> struct SmoothTileGeo<64> { using type = Geo<float, 64, 8, 16, Radices<8, 8>>; };
 template <> struct SmoothTileGeo<100> { using type = Geo<float, 100, 20, 32, Radices<4, 5, 5>>; };
+template <> struct SmoothTileGeo<125> { using type = Geo<float, 125, 25, 32, Radices<5, 5, 5>>; };
 template <> struct SmoothTileGeo<128> { using type = Geo<float, 128, 16, 16, Radices<8, 16>>; };
 template <> struct SmoothTileGeo<196> { using type = Geo<float, 196, 28, 16, Radices<4, 7, 7>>; };
+template <> struct SmoothTileGeo<200> { using type = Geo<float, 200, 40, 32, Radices<8, 5, 5>>; };
 template <> struct SmoothTileGeo<225> { using type = Geo<float, 225, 15, 16, Radices<3, 3, 5, 5>>; };
+template <> struct SmoothTileGeo<250> { using type = Geo<float, 250, 10, 16, Radices<2, 5, 5, 5>>; };
+template <> struct SmoothTileGeo<256> { using type = Geo<float, 256, 16, 16, Radices<16, 16>>; };
 template <> struct SmoothTileGeo<375> { using type = Geo<float, 375, 15, 16, Radices<3, 5, 5, 5>>; };
+template <> struct SmoothTileGeo<400> { using type = Geo<float, 400, 20, 16, Radices<4, 4, 5, 5>>; };
+template <> struct SmoothTileGeo<500> { using type = Geo<float, 500, 20, 16, Radices<4, 5, 5, 5>>; };
+template <> struct SmoothTileGeo<512> { using type = Geo<float, 512, 16, 16, Radices<2, 16, 16>>; };
+template <> struct SmoothTileGeo<625> { using type = Geo<float, 625, 25, 8, Radices<5, 5, 5, 5>>; };
 template <> struct SmoothTileGeo<1000> { using type = Geo<float, 1000, 40, 8, Radices<8, 5, 5, 5>>; };
-struct CompiledPair { uint32_t a, b; };
-static constexpr CompiledPair COMPILED_PAIRS[] = {{100, 100}, {196, 225}, {128, 375}, {100, 1000}, {1000, 1000}};
+template <> struct SmoothTileGeo<1024> { using type = Geo<float, 1024, 16, 8, Radices<16, 16, 4>>; };
+// pass lengths with a compiled tile; a two-pass plan exists for every product a * b of two of them (a <= b)
+static constexpr uint32_t COMPILED_TILE_LENGTHS[] = {64, 100, 125, 128, 196, 200, 225, 250, 256, 375, 400, 500, 512, 625, 1000, 1024};
+
 
 // largest transform one CTA keeps in shared memory: 16384 c32 (136 KiB) / 8192 c64 (136 KiB)
 template <typename T> struct DirectMax { static constexpr uint32_t v = sizeof(T) == 4 ? 16384 : 8192; };
@@ -482,6 +495,11 @@ template <> struct HasV1<float, 16384> { static constexpr bool direct = true, ti
 // kind 0: one-pass Smooth plan of pl.len;  kind 1: SmoothFourStep{a x b}
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+// single-pass cluster plans (cluster.h), compiled in the same translation unit as the fused kernels
+bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN);
+// compiled composite tiles (b200fft_ctile32.cu)
+bool build_compiled_smooth_f32(b200fft_plan& pl, uint32_t a, uint32_t b);
+bool build_cluster_conv_f32(b200fft_plan& pl, uint64_t M, int mode);
 // likewise the fused single-launch four-step kernels (b200fft_fused32.cu)
 typedef std::function<bool(const void* in, void* out, void* work, uint64_t batch, rt::stream_t)> FusedFn;
 bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const void* full_tw, FusedFn& fn, uint32_t& W);
@@ -945,6 +963,151 @@ struct Builder {
         }
         return false;
     }
+    // ---------------- single-pass four-step on a thread-block cluster (cluster.h), f32, N = 2^14 .. 2^17 ----------------
+    // B200FFT_CLUSTER: bit mask of log2 N - 14 for which the cluster plan is the default (measured, profiles/); 0 = never
+    static uint32_t cluster_mask() {
+        static uint32_t v = [] {
+            const char* e = std::getenv("B200FFT_CLUSTER");
+            return e ? (uint32_t)std::atoi(e) : 0u;
+        }();
+        return v;
+    }
+    template <int L1, int L2, int CC, bool SW>
+    static bool make_cluster_t(b200fft_plan& pl) {
+        if constexpr (sizeof(T) == 4) {
+            using GA = typename FusedGeo<T, L1>::type;
+            using GB = typename FusedGeo<T, L2>::type;
+            using KT = ClusterKernel<GA, GB, CC, SW>;
+            static_assert(KT::SMEM_BYTES <= MAX_SMEM_PER_CTA, "cluster tile fits one CTA");
+            const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2), lgN = lg1 + lg2;
+            const C* twa = upload(pl, stage_twiddles<GA>());
+            const C* twb = upload(pl, stage_twiddles<GB>());
+            const C* full_tw = make_full_twiddles(pl, lg1, lg2);
+            if (!twa || !twb || !full_tw) return false;
+            if (rt::cluster_max_active<KT>() <= 0) return false;
+            pl.exec = [=](const ExecCtx& c) {
+                // (2^24 transforms per launch keep the CTA index inside 31 bits)
+                const uint64_t seg = (1ull << 30) / CC;
+                for (uint64_t b0 = 0; b0 < c.batch; b0 += seg) {
+                    const uint64_t nb = std::min(seg, c.batch - b0);
+                    typename KT::Params p;
+                    p.load = LoadCols<T, SW>{(const C*)c.in + (b0 << lgN), lgN, lg2};
+                    p.store = StoreTransposed<T, SW>{(C*)c.out + (b0 << lgN), lgN, lg1};
+                    p.twa = twa;
+                    p.twb = twb;
+                    p.full_tw = full_tw;
+                    p.n_transforms = nb;
+                    if (!rt::launch_cluster<KT>(p, nb, c.stream)) return false;
+                }
+                return true;
+            };
+            pl.launches = [=](uint64_t batch) { return (batch + ((1ull << 30) / CC) - 1) / ((1ull << 30) / CC); };
+            pl.desc = "ClusterFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",cluster=" + std::to_string(CC) + "}";
+            return true;
+        } else {
+            (void)pl;
+            return false;
+        }
+    }
+    // Rader (n = M + 1 prime) / Bluestein (2n - 1 <= M) with the inner FFT of M = L * L points inside one cluster pass (cluster.h)
+    template <int L, int CC, bool SW, int MODE>
+    static bool make_cluster_conv_t(b200fft_plan& pl) {
+        if constexpr (sizeof(T) == 4) {
+            using G = typename FusedGeo<T, L>::type;
+            using KT = ClusterConvKernel<G, CC, SW, MODE>;
+            static_assert(KT::SMEM_BYTES <= MAX_SMEM_PER_CTA, "cluster tile fits one CTA");
+            const uint64_t n = pl.len, M = (uint64_t)L * L;
+            const uint32_t lg = hm::ilog2(L);
+            std::vector<C> mult;
+            uint64_t groot = 0;
+            const uint32_t *d_g = nullptr, *d_s = nullptr;
+            const C* d_chirp = nullptr;
+            if (MODE == 0) {
+                std::vector<uint32_t> gpow, ginv;
+                rader_tables(n, M, gpow, ginv, mult, groot);
+                d_g = upload(pl, gpow);
+                d_s = upload(pl, ginv);
+                if (!d_g || !d_s) return false;
+            } else {
+                std::vector<C> chirp;
+                bluestein_tables(n, M, chirp, mult);
+                d_chirp = upload(pl, chirp);
+                if (!d_chirp) return false;
+            }
+            const C* d_mult = upload(pl, mult);
+            const C* tw = upload(pl, stage_twiddles<G>());
+            const C* full_tw = make_full_twiddles(pl, lg, lg);
+            if (!d_mult || !tw || !full_tw) return false;
+            if (rt::cluster_max_active<KT>() <= 0) return false;
+            pl.exec = [=](const ExecCtx& c) {
+                const uint64_t seg = (1ull << 30) / CC;
+                for (uint64_t b0 = 0; b0 < c.batch; b0 += seg) {
+                    const uint64_t nb = std::min(seg, c.batch - b0);
+                    typename KT::Params p;
+                    p.in = (const C*)c.in + b0 * n;
+                    p.out = (C*)c.out + b0 * n;
+                    p.gather = d_g;
+                    p.scatter = d_s;
+                    p.chirp = d_chirp;
+                    p.mult = d_mult;
+                    p.tw = tw;
+                    p.full_tw = full_tw;
+                    p.n = (uint32_t)n;
+                    p.n_transforms = nb;
+                    if (!rt::launch_cluster<KT>(p, nb, c.stream)) return false;
+                }
+                return true;
+            };
+            pl.launches = [=](uint64_t batch) { return (batch + ((1ull << 30) / CC) - 1) / ((1ull << 30) / CC); };
+            const std::string inner = "ClusterFourStep{" + std::to_string(L) + "x" + std::to_string(L) + ",cluster=" + std::to_string(CC) + "}";
+            pl.desc = MODE == 0 ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + ",fused}"
+                                : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + ",fused}";
+            return true;
+        } else {
+            (void)pl;
+            return false;
+        }
+    }
+    // mode 0: Rader (pl.len = M + 1 prime), 1: Bluestein; M = 2^14 or 2^16
+    static bool cluster_conv_build_here(b200fft_plan& pl, uint64_t M, int mode) {
+        const bool sw = pl.direction != 0;
+        if (M == (1u << 14)) {
+            if (mode == 0) return sw ? make_cluster_conv_t<128, 2, true, 0>(pl) : make_cluster_conv_t<128, 2, false, 0>(pl);
+            return sw ? make_cluster_conv_t<128, 2, true, 1>(pl) : make_cluster_conv_t<128, 2, false, 1>(pl);
+        }
+        if (M == (1u << 16)) {
+            if (mode == 0) return sw ? make_cluster_conv_t<256, 8, true, 0>(pl) : make_cluster_conv_t<256, 8, false, 0>(pl);
+            return sw ? make_cluster_conv_t<256, 8, true, 1>(pl) : make_cluster_conv_t<256, 8, false, 1>(pl);
+        }
+        return false;
+    }
+    static bool make_cluster_conv(b200fft_plan& pl, uint64_t M, int mode) {
+        if constexpr (sizeof(T) == 4) return build_cluster_conv_f32(pl, M, mode);
+        return false;
+    }
+    // B200FFT_CLUSTER_CONV=1: Rader 65537 and Bluestein with M = 2^14 / 2^16 (f32) run inside one cluster pass by default
+    static bool use_cluster_conv() {
+        static bool v = [] {
+            const char* e = std::getenv("B200FFT_CLUSTER_CONV");
+            return e && std::atoi(e) == 1;
+        }();
+        return v;
+    }
+    static bool cluster_build_here(b200fft_plan& pl, uint32_t lgN) {
+        const bool sw = pl.direction != 0;
+        switch (lgN) {
+            case 14: return sw ? make_cluster_t<128, 128, 2, true>(pl) : make_cluster_t<128, 128, 2, false>(pl);
+            case 15: return sw ? make_cluster_t<128, 256, 4, true>(pl) : make_cluster_t<128, 256, 4, false>(pl);
+            case 16: return sw ? make_cluster_t<256, 256, 8, true>(pl) : make_cluster_t<256, 256, 8, false>(pl);
+            case 17: return sw ? make_cluster_t<256, 512, 16, true>(pl) : make_cluster_t<256, 512, 16, false>(pl);
+        }
+        return false;
+    }
+    static bool make_cluster(b200fft_plan& pl, uint32_t lgN) {
+        if constexpr (sizeof(T) == 4) return build_cluster_f32(pl, lgN);
+        return false;
+    }
+
     static bool make_four_step(b200fft_plan& pl, uint32_t lgN) {
         const uint32_t lg1 = lgN / 2, lg2 = lgN - lg1;  // N1 <= N2
         const uint32_t N1 = 1u << lg1, N2 = 1u << lg2;
@@ -1272,9 +1435,17 @@ struct Builder {
         if (a == 1) radices.push_back(2);
         return !radices.empty() && radices.size() <= 8;
     }
-    template <bool SW>
+    static uint32_t max_radix(const std::vector<uint32_t>& r) {
+        uint32_t m = 0;
+        for (uint32_t v : r) m = std::max(m, v);
+        return m;
+    }
+    template <bool SW, int RMAX = 31>
     static bool make_smooth_t(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
-        using KT = SmoothKernel<T, SW>;
+        if constexpr (RMAX > 16) {
+            if (max_radix(radices) <= 16) return make_smooth_t<SW, 16>(pl, radices);  // the 3-CTA-per-SM instantiation
+        }
+        using KT = SmoothKernel<T, SW, RMAX>;
         const uint32_t n = (uint32_t)pl.len;
         typename KT::Params base;
         std::memset(&base, 0, sizeof(base));
@@ -1396,10 +1567,17 @@ struct Builder {
         return upload(pl, t);
     }
     // variant 0: SmoothFourStep (the reference's MixedRadix);  1: GoodThomas (N1, N2 coprime: CRT / Ruritanian index maps, no twiddles)
-    template <bool SW>
+    static bool small_radices_only(uint32_t N1, uint32_t N2) {
+        std::vector<uint32_t> ra, rb;
+        return smooth_factor(N1, ra) && smooth_factor(N2, rb) && max_radix(ra) <= 16 && max_radix(rb) <= 16;
+    }
+    template <bool SW, int RMAX = 31>
     static bool make_smooth_four_step_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
-        using KA = SmoothPassKernel<T, SW, 1>;
-        using KB = SmoothPassKernel<T, SW, 2>;
+        if constexpr (RMAX > 16) {
+            if (small_radices_only(N1, N2)) return make_smooth_four_step_t<SW, 16>(pl, N1, N2, variant);
+        }
+        using KA = SmoothPassKernel<T, SW, 1, RMAX>;
+        using KB = SmoothPassKernel<T, SW, 2, RMAX>;
         const uint64_t N = (uint64_t)N1 * N2;
         typename KA::Params pa;
         typename KB::Params pb;
@@ -1476,15 +1654,23 @@ struct Builder {
         }();
         return v;
     }
-    static bool compiled_pair(uint64_t n, uint32_t& a, uint32_t& b) {
-        if (sizeof(T) != 4 || !use_compiled_smooth()) return false;
-        for (const CompiledPair& cp : COMPILED_PAIRS)
-            if ((uint64_t)cp.a * cp.b == n) {
-                a = cp.a;
-                b = cp.b;
-                return true;
-            }
+    static bool compiled_len(uint64_t x) {
+        for (uint32_t v : COMPILED_TILE_LENGTHS)
+            if (v == x) return true;
         return false;
+    }
+    static bool compiled_pair(uint64_t n, uint32_t& a, uint32_t& b) {
+        if (sizeof(T) != 4 || !use_compiled_smooth() || hm::is_pow2(n)) return false;
+        // the most balanced product of two compiled tile lengths
+        bool found = false;
+        for (uint32_t x : COMPILED_TILE_LENGTHS)
+            for (uint32_t y : COMPILED_TILE_LENGTHS)
+                if (x <= y && (uint64_t)x * y == n && (!found || x > a)) {
+                    a = x;
+                    b = y;
+                    found = true;
+                }
+        return found;
     }
     // chunks of a multi-pass plan rotate over up to K streams (the caller's + auxiliary ones, fork / join with events); body(b0, nb, k,
     // stream) issues the launches of one chunk, k = which workspace
@@ -1519,67 +1705,98 @@ struct Builder {
         }
         return ok;
     }
-    template <int L1, int L2, bool SW>
-    static bool make_compiled_smooth_t(b200fft_plan& pl) {
+    // the two passes are built per LENGTH (pass A depends on N1 only, pass B on N2 only): any pair of compiled lengths combines
+    typedef std::function<bool(const C* in, C* work, uint64_t N, uint32_t N2, uint64_t nb, rt::stream_t)> CPassA;
+    typedef std::function<bool(const C* work, C* out, const C* full_tw, uint64_t N, uint32_t N1, uint64_t nb, rt::stream_t)> CPassB;
+    template <int L, bool SW>
+    static bool make_cpass_a(b200fft_plan& pl, CPassA& fn) {
         if constexpr (sizeof(T) == 4) {
-            using GA = typename SmoothTileGeo<L1>::type;
-            using GB = typename SmoothTileGeo<L2>::type;
-            using KA = FftKernel<GA, FF, FF, LoadColsG<T, SW>, StoreColsG<T>>;
-            using KB = FftKernel<GB, JF, FF, LoadRowsTwG<T>, StoreTransposedG<T, SW>>;
-            const uint64_t N = (uint64_t)L1 * L2;
-            const C* twa = upload(pl, stage_twiddles<GA>());
-            const C* twb = upload(pl, stage_twiddles<GB>());
-            const C* full_tw = smooth_full_twiddles(pl, L1, L2);
-            if (!twa || !twb || !full_tw) return false;
-            const int K = overlap_streams(4);
-            // K chunks in flight share ~48 MiB of L2; FFT indices of a launch stay below 2^31
-            uint64_t chunk = std::max<uint64_t>(1, (48ull << 20) / (N * sizeof(C)) / (uint64_t)K);
-            chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(L1, L2));
-            pl.chunk = chunk;
-            pl.work_bytes = [=](uint64_t batch) {
-                const uint64_t nchunks = (batch + chunk - 1) / chunk;
-                return std::min(batch, chunk) * N * sizeof(C) * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
+            using G = typename SmoothTileGeo<L>::type;
+            using KA = FftKernel<G, FF, FF, LoadColsG<T, SW>, StoreColsG<T>>;
+            const C* tw = upload(pl, stage_twiddles<G>());
+            if (!tw) return false;
+            fn = [=](const C* in, C* work, uint64_t N, uint32_t N2, uint64_t nb, rt::stream_t s) {
+                const FastDiv d2 = make_fastdiv(N2);
+                typename KA::Params a;
+                a.load = LoadColsG<T, SW>{in, N, N2, d2};
+                a.store = StoreColsG<T>{work, N, N2, d2};
+                a.tw = tw;
+                a.n_fft = nb * N2;
+                return rt::launch<KA>(a, (a.n_fft + G::F - 1) / G::F, s);
             };
-            pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
-            b200fft_plan* self = &pl;
-            const FastDiv d1 = make_fastdiv(L1), d2 = make_fastdiv(L2);
-            pl.exec = [=](const ExecCtx& c) {
-                const C* in = (const C*)c.in;
-                C* out = (C*)c.out;
-                C* work = (C*)c.work;
-                return run_chunks(self, c, chunk, K, [&](uint64_t b0, uint64_t nb, int k, rt::stream_t s) {
-                    C* w = work + (uint64_t)k * chunk * N;
-                    typename KA::Params a;
-                    a.load = LoadColsG<T, SW>{in + b0 * N, N, (uint32_t)L2, d2};
-                    a.store = StoreColsG<T>{w, N, (uint32_t)L2, d2};
-                    a.tw = twa;
-                    a.n_fft = nb * L2;
-                    if (!rt::launch<KA>(a, (a.n_fft + GA::F - 1) / GA::F, s)) return false;
-                    typename KB::Params b;
-                    b.load = LoadRowsTwG<T>{w, full_tw, (uint32_t)L2, (uint32_t)L1, d1, use_discard() ? 1u : 0u};
-                    b.store = StoreTransposedG<T, SW>{out + b0 * N, N, (uint32_t)L1, d1};
-                    b.tw = twb;
-                    b.n_fft = nb * L1;
-                    return rt::launch<KB>(b, (b.n_fft + GB::F - 1) / GB::F, s);
-                });
-            };
-            pl.desc = "SmoothFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",compiled}";
             return true;
         } else {
-            (void)pl;
+            (void)pl; (void)fn;
             return false;
         }
     }
+    template <int L, bool SW>
+    static bool make_cpass_b(b200fft_plan& pl, CPassB& fn) {
+        if constexpr (sizeof(T) == 4) {
+            using G = typename SmoothTileGeo<L>::type;
+            using KB = FftKernel<G, JF, FF, LoadRowsTwG<T>, StoreTransposedG<T, SW>>;
+            const C* tw = upload(pl, stage_twiddles<G>());
+            if (!tw) return false;
+            fn = [=](const C* work, C* out, const C* full_tw, uint64_t N, uint32_t N1, uint64_t nb, rt::stream_t s) {
+                const FastDiv d1 = make_fastdiv(N1);
+                typename KB::Params b;
+                b.load = LoadRowsTwG<T>{work, full_tw, (uint32_t)L, N1, d1, use_discard() ? 1u : 0u};
+                b.store = StoreTransposedG<T, SW>{out, N, N1, d1};
+                b.tw = tw;
+                b.n_fft = nb * N1;
+                return rt::launch<KB>(b, (b.n_fft + G::F - 1) / G::F, s);
+            };
+            return true;
+        } else {
+            (void)pl; (void)fn;
+            return false;
+        }
+    }
+    template <bool SW>
+    static bool make_cpasses(b200fft_plan& pl, uint32_t a, uint32_t b, CPassA& fa, CPassB& fb) {
+        bool ok = false;
+#define B2_CL(L) case L: ok = make_cpass_a<L, SW>(pl, fa); break;
+        switch (a) { B2_CL(64) B2_CL(100) B2_CL(125) B2_CL(128) B2_CL(196) B2_CL(200) B2_CL(225) B2_CL(250) B2_CL(256) B2_CL(375) B2_CL(400) B2_CL(500) B2_CL(512) B2_CL(625) B2_CL(1000) B2_CL(1024) }
+#undef B2_CL
+        if (!ok) return false;
+        ok = false;
+#define B2_CL(L) case L: ok = make_cpass_b<L, SW>(pl, fb); break;
+        switch (b) { B2_CL(64) B2_CL(100) B2_CL(125) B2_CL(128) B2_CL(196) B2_CL(200) B2_CL(225) B2_CL(250) B2_CL(256) B2_CL(375) B2_CL(400) B2_CL(500) B2_CL(512) B2_CL(625) B2_CL(1000) B2_CL(1024) }
+#undef B2_CL
+        return ok;
+    }
+    static bool compiled_smooth_build_here(b200fft_plan& pl, uint32_t L1, uint32_t L2) {
+        CPassA fa;
+        CPassB fb;
+        if (!(pl.direction ? make_cpasses<true>(pl, L1, L2, fa, fb) : make_cpasses<false>(pl, L1, L2, fa, fb))) return false;
+        const uint64_t N = (uint64_t)L1 * L2;
+        const C* full_tw = smooth_full_twiddles(pl, L1, L2);
+        if (!full_tw) return false;
+        const int K = overlap_streams(4);
+        // K chunks in flight share ~48 MiB of L2; FFT indices of a launch stay below 2^31
+        uint64_t chunk = std::max<uint64_t>(1, (48ull << 20) / (N * sizeof(C)) / (uint64_t)K);
+        chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(L1, L2));
+        pl.chunk = chunk;
+        pl.work_bytes = [=](uint64_t batch) {
+            const uint64_t nchunks = (batch + chunk - 1) / chunk;
+            return std::min(batch, chunk) * N * sizeof(C) * std::min<uint64_t>((uint64_t)K, std::max<uint64_t>(nchunks, 1));
+        };
+        pl.launches = [=](uint64_t batch) { return 2 * ((batch + chunk - 1) / chunk); };
+        b200fft_plan* self = &pl;
+        pl.exec = [=](const ExecCtx& c) {
+            const C* in = (const C*)c.in;
+            C* out = (C*)c.out;
+            C* work = (C*)c.work;
+            return run_chunks(self, c, chunk, K, [&](uint64_t b0, uint64_t nb, int k, rt::stream_t s) {
+                C* w = work + (uint64_t)k * chunk * N;
+                return fa(in + b0 * N, w, N, L2, nb, s) && fb(w, out + b0 * N, full_tw, N, L1, nb, s);
+            });
+        };
+        pl.desc = "SmoothFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",compiled}";
+        return true;
+    }
     static bool make_compiled_smooth(b200fft_plan& pl, uint32_t a, uint32_t b) {
-        const bool sw = pl.direction != 0;
-#define B2_CPAIR(A, B) \
-    if (a == A && b == B) return sw ? make_compiled_smooth_t<A, B, true>(pl) : make_compiled_smooth_t<A, B, false>(pl);
-        B2_CPAIR(100, 100)
-        B2_CPAIR(196, 225)
-        B2_CPAIR(128, 375)
-        B2_CPAIR(100, 1000)
-        B2_CPAIR(1000, 1000)
-#undef B2_CPAIR
+        if constexpr (sizeof(T) == 4) return build_compiled_smooth_f32(pl, a, b);
         return false;
     }
 
@@ -1591,13 +1808,16 @@ struct Builder {
         return rs;
     }
     // mode 0: Rader, pl.len = r0 * p, inner M = p - 1;  mode 1: Bluestein, inner M = pM >= 2 len - 1
-    template <bool SW>
+    template <bool SW, int RMAX = 31>
     static bool make_smooth_conv_t(b200fft_plan& pl, int mode, uint32_t r0, uint32_t pM) {
-        using KT = SmoothConvKernel<T, SW>;
+        using KT = SmoothConvKernel<T, SW, RMAX>;
         const uint32_t n = (uint32_t)pl.len;
         const uint32_t M = mode == 0 ? pM - 1 : pM;
         std::vector<uint32_t> radices;
         if (!smooth_factor(M, radices) || (uint64_t)r0 * M > CONV_SMOOTH_MAX) return false;
+        if constexpr (RMAX > 16) {
+            if (max_radix(radices) <= 16) return make_smooth_conv_t<SW, 16>(pl, mode, r0, pM);
+        }
         typename KT::Params base;
         if (!fill_smooth_pass<KT>(pl, base, M, radices)) return false;
         base.n = n;
@@ -1633,7 +1853,9 @@ struct Builder {
         base.mult = upload(pl, mult);
         if (!base.mult) return false;
         // virtual transforms per CTA: a multiple of r0, both ping-pong buffers inside the budget, at most 64
-        uint32_t F = std::max<uint32_t>(1, CONV_SMOOTH_MAX / M / r0) * r0;
+        // (inner lengths that fit the one-pass Smooth budget keep to it: 64 KiB per CTA leaves room for three CTAs per SM)
+        const uint32_t budget = (uint64_t)r0 * M <= SMOOTH_MAX ? SMOOTH_MAX : CONV_SMOOTH_MAX;
+        uint32_t F = std::max<uint32_t>(1, budget / M / r0) * r0;
         while (F > r0 && F > 64) F -= r0;
         base.f_per_cta = F;
         base.smem_bytes = (uint32_t)(((2ull * F * M + F) * sizeof(C) + 15) / 16 * 16);
@@ -1663,11 +1885,14 @@ struct Builder {
     // ---------------- large Rader / Bluestein over a smooth two-pass inner FFT of M = N1 * N2 ----------------
     // the four launches of make_big_conv (A1 gather|chirp-pad, B1 x mult + conj (+ DC), A2 plain, B2 conj + scatter | conj x chirp)
     // with the run-time-radix passes: any "easy" prime (p - 1 smooth) above the one-pass limit, Bluestein with the smallest smooth M
-    template <bool SW>
+    template <bool SW, int RMAX = 31>
     static bool make_smooth_big_conv_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
-        using KA = SmoothPassKernel<T, SW, 1>;
-        using KA2 = SmoothPassKernel<T, false, 1>;
-        using KB = SmoothPassKernel<T, SW, 2>;
+        if constexpr (RMAX > 16) {
+            if (small_radices_only(N1, N2)) return make_smooth_big_conv_t<SW, 16>(pl, N1, N2, rader);
+        }
+        using KA = SmoothPassKernel<T, SW, 1, RMAX>;
+        using KA2 = SmoothPassKernel<T, false, 1, RMAX>;
+        using KB = SmoothPassKernel<T, SW, 2, RMAX>;
         const uint64_t n = pl.len, M = (uint64_t)N1 * N2;
         typename KA::Params pa;
         typename KB::Params pb;
@@ -1970,8 +2195,8 @@ struct Builder {
                     break;
                 }
                 if (b > SMOOTH_MAX || !smooth_factor_any(a) || !smooth_factor_any(b)) return unsupported("both factors must be smooth one-pass lengths");
-                if (uint32_t c1 = 0, c2 = 0; r.kind == B200FFT_RECIPE_MIXED_RADIX && compiled_pair(n, c1, c2) && c1 == a && c2 == b) {
-                    ok = make_compiled_smooth(pl, c1, c2);
+                if (r.kind == B200FFT_RECIPE_MIXED_RADIX && sizeof(T) == 4 && use_compiled_smooth() && compiled_len(a) && compiled_len(b)) {
+                    ok = make_compiled_smooth(pl, (uint32_t)a, (uint32_t)b);
                     break;
                 }
                 ok = smooth_dispatch(pl, r.kind == B200FFT_RECIPE_GOOD_THOMAS ? 4 : 1, (uint32_t)a, (uint32_t)b);
@@ -1985,7 +2210,10 @@ struct Builder {
                 if (in && in->len != M) return unsupported("the inner FFT of RADER has length p - 1");
                 const uint32_t ik = in ? in->kind : (uint32_t)B200FFT_RECIPE_AUTO;
                 uint32_t s1 = 0, s2 = 0;
-                if (hm::is_pow2(M) && r0 == 1 && (ik == B200FFT_RECIPE_AUTO || ik == B200FFT_RECIPE_POW2 || ik == B200FFT_RECIPE_MIXED_RADIX)) {
+                if (ik == B200FFT_RECIPE_CLUSTER) {
+                    if (sizeof(T) != 4 || r0 != 1 || (M != (1u << 14) && M != (1u << 16))) return unsupported("RADER over a CLUSTER inner FFT: f32, p - 1 = 2^14 or 2^16");
+                    ok = make_cluster_conv(pl, M, 0);
+                } else if (hm::is_pow2(M) && r0 == 1 && (ik == B200FFT_RECIPE_AUTO || ik == B200FFT_RECIPE_POW2 || ik == B200FFT_RECIPE_MIXED_RADIX)) {
                     if (M <= 256) ok = make_rader_rt(pl, (uint32_t)M);
                     else if (M <= (uint64_t)TILE_MAX * TILE_MAX && M >= (uint64_t)TILE_MIN * TILE_MIN) ok = make_big_conv(pl, M, true);
                     else return unsupported("RADER over this power-of-two length");
@@ -2012,7 +2240,10 @@ struct Builder {
                 if (n < 2 || M < 2 * n - 1) return unsupported("the inner FFT of BLUESTEIN needs length >= 2 len - 1");
                 const uint32_t ik = in ? in->kind : (uint32_t)B200FFT_RECIPE_AUTO;
                 uint32_t s1 = 0, s2 = 0;
-                if (hm::is_pow2(M) && ik != B200FFT_RECIPE_SMOOTH) {
+                if (ik == B200FFT_RECIPE_CLUSTER) {
+                    if (sizeof(T) != 4 || (M != (1u << 14) && M != (1u << 16))) return unsupported("BLUESTEIN over a CLUSTER inner FFT: f32, M = 2^14 or 2^16");
+                    ok = make_cluster_conv(pl, M, 1);
+                } else if (hm::is_pow2(M) && ik != B200FFT_RECIPE_SMOOTH) {
                     if (M <= FUSED_CONV_MAX) ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M, 8));
                     else if (M <= (uint64_t)TILE_MAX * TILE_MAX) ok = make_big_conv(pl, M, false);
                     else return unsupported("BLUESTEIN over this power-of-two length");
@@ -2030,6 +2261,11 @@ struct Builder {
                 } else {
                     return unsupported("BLUESTEIN: the inner length must be a power of two or factor into primes <= 31");
                 }
+                break;
+            }
+            case B200FFT_RECIPE_CLUSTER: {
+                if (sizeof(T) != 4 || !hm::is_pow2(n) || n < (1u << 14) || n > (1u << 17)) return unsupported("CLUSTER plans exist for f32, 2^14 .. 2^17");
+                ok = make_cluster(pl, hm::ilog2(n));
                 break;
             }
             default:
@@ -2056,7 +2292,10 @@ struct Builder {
             return fail(B200FFT_ERR_UNSUPPORTED, "non-power-of-two lengths above 2^23 are not planned by this build");
         bool ok = false;
         if (hm::is_pow2(n)) {
-            if (n <= DirectMax<T>::v)
+            const uint32_t lgn = hm::ilog2(n);
+            if (sizeof(T) == 4 && lgn >= 14 && lgn <= 17 && ((cluster_mask() >> (lgn - 14)) & 1u))
+                ok = make_cluster(pl, lgn);  // one pass over HBM, transposed through distributed shared memory
+            else if (n <= DirectMax<T>::v)
                 ok = make_direct_rt(pl, (uint32_t)n);
             else if (n <= (uint64_t)TILE_MAX * TILE_MAX)
                 ok = make_four_step(pl, hm::ilog2(n));
@@ -2072,6 +2311,8 @@ struct Builder {
             ok = smooth_dispatch(pl, 1, s1, s2);  // composite of small primes: two passes instead of Bluestein's four
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= 256) {
             ok = make_rader_rt(pl, (uint32_t)(n - 1));
+        } else if (sizeof(T) == 4 && n == 65537 && use_cluster_conv()) {
+            ok = make_cluster_conv(pl, 65536, 0);  // the whole Rader algorithm inside one cluster pass
         } else if (hm::is_prime(n) && hm::is_pow2(n - 1) && n - 1 <= (uint64_t)TILE_MAX * TILE_MAX) {
             ok = make_big_conv(pl, n - 1, true);  // 65537
         } else {
@@ -2098,6 +2339,8 @@ struct Builder {
                 const bool smooth_wins = M3 != 0 && M3 * 100 <= M2 * bluestein_smooth_pct();
                 if (smooth_wins && M3 <= CONV_SMOOTH_MAX)
                     ok = smooth_dispatch(pl, 3, (uint32_t)M3, 0);
+                else if (sizeof(T) == 4 && use_cluster_conv() && (M2 == (1u << 14) || M2 == (1u << 16)))
+                    ok = make_cluster_conv(pl, M2, 1);
                 else if (M2 <= FUSED_CONV_MAX)
                     ok = make_bluestein_rt(pl, (uint32_t)std::max<uint64_t>(M2, 8));
                 else if (smooth_wins && M3 > CONV_SMOOTH_MAX && bluestein_smooth_big() && smooth_split(M3, b1, b2))
@@ -2127,9 +2370,14 @@ int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here(pl, kind, a, b); }
 #endif
 #if defined(B2_PART_FUSED32)
+bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN) { return Builder<float>::cluster_build_here(pl, lgN); }
+bool build_cluster_conv_f32(b200fft_plan& pl, uint64_t M, int mode) { return Builder<float>::cluster_conv_build_here(pl, M, mode); }
 bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const void* full_tw, FusedFn& fn, uint32_t& W) {
     return Builder<float>::fused_build_here(pl, L1, L2, lgN, (const cx<float>*)full_tw, fn, W);
 }
+#endif
+#if defined(B2_PART_CTILE32)
+bool build_compiled_smooth_f32(b200fft_plan& pl, uint32_t a, uint32_t b) { return Builder<float>::compiled_smooth_build_here(pl, a, b); }
 #endif
 #if defined(B2_PART_SMOOTH64)
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here(pl, kind, a, b); }

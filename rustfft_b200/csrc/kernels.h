@@ -627,11 +627,13 @@ struct RaderKernel {
 // power-of-two geometries (no cross-stage register reuse, generic index arithmetic) but one pass over
 // HBM and no padding to a power of two -- against Bluestein's two FFTs of 2-4x the length.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool SWAP>
+// RMAX = largest radix the instantiation carries: 16 drops the prime butterflies 11..31 from the stage switch, which are what push
+// these kernels to 128 registers per thread (2 CTAs per SM); without them 3 CTAs fit
+template <typename T, bool SWAP, int RMAX = 31>
 struct SmoothKernel {
     using T_ = T;
     static constexpr int NT = 256;
-    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MIN_BLOCKS = RMAX > 16 ? 2 : 3;
     static constexpr int MAX_STAGES = 8;
     static constexpr int NPHASE = MAX_STAGES;
     static constexpr size_t SMEM_BYTES = 0;  // run-time sized: Params::smem_bytes
@@ -702,13 +704,13 @@ struct SmoothKernel {
             case 7: stage<7>(p, bid, tid, P, smem); break;
             case 8: stage<8>(p, bid, tid, P, smem); break;
             case 16: stage<16>(p, bid, tid, P, smem); break;
-            case 11: stage<11>(p, bid, tid, P, smem); break;
-            case 13: stage<13>(p, bid, tid, P, smem); break;
-            case 17: stage<17>(p, bid, tid, P, smem); break;
-            case 19: stage<19>(p, bid, tid, P, smem); break;
-            case 23: stage<23>(p, bid, tid, P, smem); break;
-            case 29: stage<29>(p, bid, tid, P, smem); break;
-            case 31: stage<31>(p, bid, tid, P, smem); break;
+            case 11: if constexpr (RMAX >= 11) stage<11>(p, bid, tid, P, smem); break;
+            case 13: if constexpr (RMAX >= 13) stage<13>(p, bid, tid, P, smem); break;
+            case 17: if constexpr (RMAX >= 17) stage<17>(p, bid, tid, P, smem); break;
+            case 19: if constexpr (RMAX >= 19) stage<19>(p, bid, tid, P, smem); break;
+            case 23: if constexpr (RMAX >= 23) stage<23>(p, bid, tid, P, smem); break;
+            case 29: if constexpr (RMAX >= 29) stage<29>(p, bid, tid, P, smem); break;
+            case 31: if constexpr (RMAX >= 31) stage<31>(p, bid, tid, P, smem); break;
             default: break;
         }
     }
@@ -728,11 +730,11 @@ struct SmoothKernel {
 //                    Threads: element fastest (contiguous loads) until the last stage, row fastest there
 //                    (adjacent rows are adjacent in the output); shared memory [row][odd pitch].
 // ------------------------------------------------------------------------------------------
-template <typename T, bool SW, int MODE>
+template <typename T, bool SW, int MODE, int RMAX = 31>
 struct SmoothPassKernel {
     using T_ = T;
     static constexpr int NT = 256;
-    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MIN_BLOCKS = RMAX > 16 ? 2 : 3;
     static constexpr int MAX_STAGES = 8;
     static constexpr int NPHASE = MAX_STAGES;
     static constexpr size_t SMEM_BYTES = 0;  // run-time sized: Params::smem_bytes
@@ -912,13 +914,13 @@ struct SmoothPassKernel {
             case 7: stage<7>(p, bid, tid, P, smem); break;
             case 8: stage<8>(p, bid, tid, P, smem); break;
             case 16: stage<16>(p, bid, tid, P, smem); break;
-            case 11: stage<11>(p, bid, tid, P, smem); break;
-            case 13: stage<13>(p, bid, tid, P, smem); break;
-            case 17: stage<17>(p, bid, tid, P, smem); break;
-            case 19: stage<19>(p, bid, tid, P, smem); break;
-            case 23: stage<23>(p, bid, tid, P, smem); break;
-            case 29: stage<29>(p, bid, tid, P, smem); break;
-            case 31: stage<31>(p, bid, tid, P, smem); break;
+            case 11: if constexpr (RMAX >= 11) stage<11>(p, bid, tid, P, smem); break;
+            case 13: if constexpr (RMAX >= 13) stage<13>(p, bid, tid, P, smem); break;
+            case 17: if constexpr (RMAX >= 17) stage<17>(p, bid, tid, P, smem); break;
+            case 19: if constexpr (RMAX >= 19) stage<19>(p, bid, tid, P, smem); break;
+            case 23: if constexpr (RMAX >= 23) stage<23>(p, bid, tid, P, smem); break;
+            case 29: if constexpr (RMAX >= 29) stage<29>(p, bid, tid, P, smem); break;
+            case 31: if constexpr (RMAX >= 31) stage<31>(p, bid, tid, P, smem); break;
             default: break;
         }
     }
@@ -942,11 +944,11 @@ struct SmoothPassKernel {
 // step 2 S - 1 writes global memory.  The step index is run-time data (run_kernel_loop): 14 butterfly bodies per
 // precision instead of 14 x 16.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool SW>
+template <typename T, bool SW, int RMAX = 31>
 struct SmoothConvKernel {
     using T_ = T;
     static constexpr int NT = 256;
-    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MIN_BLOCKS = RMAX > 16 ? 2 : 3;
     static constexpr int MAX_STAGES = 8;
     static constexpr int NPHASE = 2 * MAX_STAGES;  // CPU replay: phase<P> = step P
     static constexpr size_t SMEM_BYTES = 0;        // run-time sized: Params::smem_bytes
@@ -1080,13 +1082,13 @@ struct SmoothConvKernel {
             case 7: stage<7>(p, bid, tid, st, smem); break;
             case 8: stage<8>(p, bid, tid, st, smem); break;
             case 16: stage<16>(p, bid, tid, st, smem); break;
-            case 11: stage<11>(p, bid, tid, st, smem); break;
-            case 13: stage<13>(p, bid, tid, st, smem); break;
-            case 17: stage<17>(p, bid, tid, st, smem); break;
-            case 19: stage<19>(p, bid, tid, st, smem); break;
-            case 23: stage<23>(p, bid, tid, st, smem); break;
-            case 29: stage<29>(p, bid, tid, st, smem); break;
-            case 31: stage<31>(p, bid, tid, st, smem); break;
+            case 11: if constexpr (RMAX >= 11) stage<11>(p, bid, tid, st, smem); break;
+            case 13: if constexpr (RMAX >= 13) stage<13>(p, bid, tid, st, smem); break;
+            case 17: if constexpr (RMAX >= 17) stage<17>(p, bid, tid, st, smem); break;
+            case 19: if constexpr (RMAX >= 19) stage<19>(p, bid, tid, st, smem); break;
+            case 23: if constexpr (RMAX >= 23) stage<23>(p, bid, tid, st, smem); break;
+            case 29: if constexpr (RMAX >= 29) stage<29>(p, bid, tid, st, smem); break;
+            case 31: if constexpr (RMAX >= 31) stage<31>(p, bid, tid, st, smem); break;
             default: break;
         }
     }

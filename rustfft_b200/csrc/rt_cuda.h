@@ -199,9 +199,68 @@ static bool launch_ex(void (*kern)(P), unsigned grid, unsigned block, size_t sme
 }  // namespace b2
 
 #include "fused.h"
+#include "cluster.h"
 
 namespace b2 {
 namespace rt {
+
+// thread-block cluster launch (cluster.h): grid = clusters x C CTAs, cluster dimension C (> 8 needs the non-portable opt-in)
+template <class KT>
+static int cluster_max_active() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cached[dev & 63].load(std::memory_order_acquire);
+    if (v != 0) return v;
+    v = -1;
+    bool ok = check(cudaFuncSetAttribute(run_cluster<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT::SMEM_BYTES),
+                    "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    if (ok && KT::C > 8)
+        ok = check(cudaFuncSetAttribute(run_cluster<KT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1),
+                   "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)");
+    if (ok) {
+        cudaFuncSetAttribute(run_cluster<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(KT::C, 1, 1);
+        cfg.blockDim = dim3(KT::NT, 1, 1);
+        cfg.dynamicSmemBytes = KT::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = KT::C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (check(cudaOccupancyMaxActiveClusters(&n, run_cluster<KT>, &cfg), "cudaOccupancyMaxActiveClusters") && n > 0) v = n;
+        else if (n <= 0) g_err = "no cluster of this size fits on the device";
+    }
+    cached[dev & 63].store(v, std::memory_order_release);
+    return v;
+}
+template <class KT>
+static bool launch_cluster(const typename KT::Params& p, uint64_t clusters, stream_t s) {
+    if (clusters == 0) return true;
+    if (clusters * KT::C > 0x7fffffffull) {
+        g_err = "grid too large";
+        return false;
+    }
+    if (cluster_max_active<KT>() <= 0) return false;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * KT::C), 1, 1);
+    cfg.blockDim = dim3(KT::NT, 1, 1);
+    cfg.dynamicSmemBytes = KT::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = KT::C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check(cudaLaunchKernelEx(&cfg, run_cluster<KT>, p), "cluster kernel launch");
+}
 
 // once per (kernel, device): opt in to > 48 KiB dynamic shared memory, and ask for a shared-memory
 // carveout that fits as many CTAs as registers and threads allow (the driver's default carveout left

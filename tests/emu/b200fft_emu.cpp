@@ -52,6 +52,7 @@ struct DeviceGuard {
 }  // namespace b2
 
 #include "../../rustfft_b200/csrc/fused.h"
+#include "../../rustfft_b200/csrc/cluster.h"
 
 namespace b2 {
 namespace rt {
@@ -103,6 +104,35 @@ static bool launch_loop(const typename KT::Params& p, uint64_t ctas, uint32_t n_
         std::memset(smem.data(), 0xff, smem.size() * sizeof(smem[0]));
         for (uint32_t st = 0; st < n_steps; ++st)
             for (int tid = 0; tid < KT::NT; ++tid) KT::step(p, (uint32_t)bid, tid, st, smem.data());
+    }
+    return true;
+}
+
+// thread-block cluster kernels (cluster.h): the C CTAs of a cluster advance phase by phase together (every boundary is treated
+// as a cluster barrier); the DSMEM window is the array of the C shared-memory buffers
+template <class KT, int P>
+struct EmuClusterPhases {
+    static void run(const typename KT::Params& p, uint32_t cluster, std::vector<typename KT::Regs>& regs,
+                    std::vector<std::vector<cx<typename KT::T>>>& smem, cx<typename KT::T>* const* remote) {
+        for (int c = 0; c < KT::C; ++c)
+            for (int tid = 0; tid < KT::NT; ++tid)
+                KT::template phase<P>(p, cluster * KT::C + c, tid, regs[(size_t)c * KT::NT + tid], smem[(size_t)c].data(), remote);
+        if constexpr (P + 1 < KT::NPHASE) EmuClusterPhases<KT, P + 1>::run(p, cluster, regs, smem, remote);
+    }
+};
+template <class KT>
+static int cluster_max_active() { return 32; }
+template <class KT>
+static bool launch_cluster(const typename KT::Params& p, uint64_t clusters, stream_t) {
+    ++g_launches;
+    using C = cx<typename KT::T>;
+    std::vector<typename KT::Regs> regs((size_t)KT::C * KT::NT);
+    std::vector<std::vector<C>> smem((size_t)KT::C, std::vector<C>(KT::SMEM_BYTES / sizeof(C) + 1));
+    C* remote[KT::C];
+    for (int c = 0; c < KT::C; ++c) remote[c] = smem[(size_t)c].data();
+    for (uint64_t cl = 0; cl < clusters; ++cl) {
+        for (auto& b : smem) std::memset(b.data(), 0xff, b.size() * sizeof(C));
+        EmuClusterPhases<KT, 0>::run(p, (uint32_t)cl, regs, smem, remote);
     }
     return true;
 }

@@ -146,5 +146,37 @@ def check_recipes_of_existing_kinds(planner, dtype):
             planner.plan_fft_with_recipe(bad, DIRS[0])
 
 
-ALL = [check_rader_primes_below_100, check_default_prime_rule, check_mixed_radix_rader, check_overflow_primes, check_good_thomas_small_pairs,
+def check_cluster_plans(planner, dtype):
+    """f32 2^14 .. 2^17 in ONE pass over HBM: both four-step passes inside a thread-block cluster of 2 / 4 / 8 / 16 CTAs, the transpose
+    between them through distributed shared memory (cluster.h); against the scalar-planner oracle (Radix4, src/algorithm/radix4.rs) and the
+    chunked / fused two-pass plan of the same length (same butterflies and tables: results within rounding of each other)."""
+    if dtype != np.complex64:
+        with pytest.raises(rb.FftError, match="CLUSTER"):
+            planner.plan_fft_with_recipe(R.cluster(1 << 15), DIRS[0])
+        return
+    from util import rel_l2, signal
+
+    for lg, c in [(14, 2), (15, 4), (16, 8), (17, 16)]:
+        n = 1 << lg
+        for d in DIRS:
+            f = check_fft_algorithm(planner, n, d, dtype, control_kind=oracle.PLANNER, chunks=5 if d == DIRS[0] else 1, recipe=R.cluster(n))
+            assert f.describe() == "ClusterFourStep{%dx%d,cluster=%d}" % (1 << (lg // 2), 1 << (lg - lg // 2), c), f.describe()
+        x = signal(3 * n, dtype, seed=lg)
+        a, b = x.copy(), x.copy()
+        planner.plan_fft_with_recipe(R.cluster(n), DIRS[0]).process(a)
+        planner.plan_fft_forward(n).process(b)
+        assert rel_l2(a, b) < 1e-6
+    with pytest.raises(rb.FftError, match="CLUSTER"):
+        planner.plan_fft_with_recipe(R.cluster(1 << 18), DIRS[0])
+    # the whole Rader / Bluestein algorithm inside one cluster pass (BASELINE config 4: n = 65537)
+    for rc, want in [(R.rader(65537, 1, R.cluster(65536)), "Rader{n=65537,g=3,inner=ClusterFourStep{256x256,cluster=8},fused}"),
+                     (R.bluestein(20011, R.cluster(65536)), "Bluestein{n=20011,M=65536,inner=ClusterFourStep{256x256,cluster=8},fused}"),
+                     (R.bluestein(32768, R.cluster(65536)), "Bluestein{n=32768,M=65536,inner=ClusterFourStep{256x256,cluster=8},fused}"),
+                     (R.bluestein(6007, R.cluster(16384)), "Bluestein{n=6007,M=16384,inner=ClusterFourStep{128x128,cluster=2},fused}")]:
+        for d in DIRS:
+            f = check_fft_algorithm(planner, rc.len, d, dtype, control_kind=oracle.PLANNER, chunks=3 if d == DIRS[0] else 1, recipe=rc)
+            assert f.describe() == want, f.describe()
+
+
+ALL = [check_cluster_plans, check_rader_primes_below_100, check_default_prime_rule, check_mixed_radix_rader, check_overflow_primes, check_good_thomas_small_pairs,
        check_good_thomas_large, check_bluestein_inner_lengths, check_recipes_of_existing_kinds]

@@ -21,8 +21,10 @@ def dirty(n, dtype):
 def check_fft_algorithm(planner, n, direction, dtype, control_kind=oracle.CONTROL, chunks=3, seed=None,
                         strict_factor=4.0, recipe=None):
     """All four entry points must agree with the oracle control under the reference's criterion
-    (mean |a-b| < 0.1) AND the strict bounds of SURVEY.md 8(c): relative L2 vs the f64 truth
-    <= 4 eps log2 N, and not worse than 2x the oracle's own error on the same input."""
+    (mean |a-b| < 0.1) AND the strict bound of SURVEY.md 8(c): relative L2 vs the f64 truth <= 4 eps log2 N -- always --
+    AND stay near the oracle's own accuracy: not worse than 2x the oracle's error on the same input, unless the error is
+    already below a quarter of the strict bound (the oracle is sometimes exceptionally accurate -- a Radix4 with f64-rounded
+    twiddles against a Bluestein here -- and the measured worst ratio over len 1..1000 is 1.8 at 0.09 of the bound)."""
     inverse = direction == rb.FftDirection.Inverse
     # recipe: the caller owns planning (b200fft_plan_create_from_recipe) -- the way the reference's unit tests build one
     # algorithm directly (e.g. RadersAlgorithm::new(inner), src/algorithm/raders_algorithm.rs:324-329)
@@ -50,7 +52,9 @@ def check_fft_algorithm(planner, n, direction, dtype, control_kind=oracle.CONTRO
     if n >= 1:
         err = rel_l2(a, ref)
         oerr = rel_l2(want, ref)
-        assert err <= max(strict_bound(n, dtype, strict_factor), 2.0 * oerr), (n, direction, err, oerr, fft.describe())
+        bound = strict_bound(n, dtype, strict_factor)
+        assert err <= bound, (n, direction, err, bound, fft.describe())
+        assert err <= 2.0 * oerr or err <= 0.25 * bound, (n, direction, err, oerr, fft.describe())
     return fft
 
 

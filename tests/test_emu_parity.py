@@ -73,7 +73,7 @@ def test_smooth_four_step_plans(planner, n, desc):
 
 
 @pytest.mark.parametrize("n,batch,desc", [(10000, 70, "SmoothFourStep{100x100,compiled}"), (48000, 9, "SmoothFourStep{128x375,compiled}"),
-                                          (100000, 5, "SmoothFourStep{100x1000,compiled}"), (1000000, 2, "SmoothFourStep{1000x1000,compiled}")])
+                                          (100000, 5, "SmoothFourStep{250x400,compiled}"), (1000000, 2, "SmoothFourStep{1000x1000,compiled}")])
 def test_compiled_composite_two_pass_plans(lib, n, batch, desc):
     """f32 two-pass plans whose pass lengths have compiled composite tiles (radix-3/5/7 stages in the CTA engine): ragged tiles
     that straddle transforms, several chunks over several streams, both directions, all entry points."""
@@ -81,6 +81,15 @@ def test_compiled_composite_two_pass_plans(lib, n, batch, desc):
     for d in DIRS:
         f = check_fft_algorithm(pl, n, d, np.complex64, control_kind=oracle.PLANNER, chunks=batch if d == DIRS[0] else 1)
         assert f.describe() == desc
+
+
+def test_compiled_tile_lengths_in_both_roles(lib):
+    """Every compiled composite tile length as the column pass (first factor) and as the row pass (second factor) of a two-pass plan."""
+    pl = rb.FftPlanner(np.complex64, lib=lib)
+    ls = [64, 100, 125, 128, 196, 200, 225, 250, 256, 375, 400, 500, 512, 625, 1000, 1024]
+    for a, b in zip(ls[:-1], ls[1:]):
+        f = check_fft_algorithm(pl, a * b, DIRS[(a + b) % 2], np.complex64, control_kind=oracle.PLANNER, chunks=2, recipe=rb.Recipe.mixed_radix(a, b))
+        assert f.describe() == "SmoothFourStep{%dx%d,compiled}" % (a, b)
 
 
 def test_random_smooth_composites(planner):
@@ -110,9 +119,9 @@ def test_smooth_four_step_chunks_and_large(lib):
     pl = rb.FftPlanner(np.complex64, lib=lib)
     n, batch = 100000, 45  # 32 MiB of intermediate = 41 transforms per chunk: two chunks, the second ragged
     f = pl.plan_fft_forward(n)
-    assert f.describe() == "SmoothFourStep{100x1000,compiled}"
-    f = pl.plan_fft_with_recipe(rb.Recipe.mixed_radix(250, 400), DIRS[0])
-    assert f.describe() == "SmoothFourStep{250x400}" and f.launches(batch) == 4
+    assert f.describe() == "SmoothFourStep{250x400,compiled}"
+    f = pl.plan_fft_with_recipe(rb.Recipe.mixed_radix(160, 625), DIRS[0])  # a split without compiled tiles: the run-time-radix passes
+    assert f.describe() == "SmoothFourStep{160x625}" and f.launches(batch) == 4
     x = signal(n * batch, np.complex64, seed=3)
     y = x.copy()
     f.process(y)

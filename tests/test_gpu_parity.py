@@ -100,7 +100,8 @@ def test_config3_f64_1234_roundtrip_batch_1024(torch_cuda):
     for b in (0, 511, 1023):
         got, xb = y[b * n:(b + 1) * n], x[b * n:(b + 1) * n]
         want = oracle.fft(xb, n)  # RadixN{[2], Raders(617)} in the scalar planner
-        assert rel_l2(got, truth(xb, n, False)) <= max(strict_bound(n, np.complex128), 2 * rel_l2(want, truth(xb, n, False)))
+        assert rel_l2(got, truth(xb, n, False)) <= strict_bound(n, np.complex128)
+        assert np.all(np.isfinite(want.view(np.float64)))
     fi.process(y)
     assert rel_l2(y / n, x) <= 2 * strict_bound(n, np.complex128)
 
@@ -118,7 +119,8 @@ def test_config4_prime_65537_batch_512(torch_cuda):
         xb = x[b * n:(b + 1) * n]
         ref = truth(xb, n, False)
         want = oracle.fft(xb, n)
-        assert rel_l2(y[b * n:(b + 1) * n], ref) <= max(strict_bound(n, np.complex64), 2 * rel_l2(want, ref))
+        assert rel_l2(y[b * n:(b + 1) * n], ref) <= strict_bound(n, np.complex64)
+        assert rel_l2(y[b * n:(b + 1) * n], want) <= 2 * strict_bound(n, np.complex64)
 
 
 @pytest.mark.parametrize("lg", [21, 22, 23, 24])
@@ -151,6 +153,17 @@ def test_round2_plan_kinds(planner, check):
     """General Rader, MixedRadix{r0 x Rader}, Good-Thomas, Bluestein over smooth lengths, caller-owned recipes (tests/plan_kinds.py)."""
     pl, dtype = planner
     check(pl, dtype)
+
+
+def test_compiled_tile_lengths_in_both_roles(torch_cuda):
+    """Every compiled composite tile length (SmoothTileGeo) as the column pass and as the row pass of a two-pass plan, many transforms."""
+    pl = rb.FftPlanner(np.complex64)
+    ls = [64, 100, 125, 128, 196, 200, 225, 250, 256, 375, 400, 500, 512, 625, 1000, 1024]
+    for a, b in zip(ls[:-1], ls[1:]):
+        for d in DIRS:
+            f = check_fft_algorithm(pl, a * b, d, np.complex64, control_kind=oracle.PLANNER, chunks=40 if a * b < 100000 else 3,
+                                    recipe=rb.Recipe.mixed_radix(a, b))
+            assert f.describe() == "SmoothFourStep{%dx%d,compiled}" % (a, b)
 
 
 @pytest.mark.parametrize("n", [4225, 5000, 6000, 10000, 17017, 29791, 44100, 48000, 100000, 196608, 1000000])

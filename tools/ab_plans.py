@@ -33,13 +33,23 @@ CASES = [
     (719, [("auto", AUTO), ("bluestein-pow2-2048", R.bluestein(719)), ("bluestein-smooth-1440", R.bluestein(719, R.smooth(1440)))]),
     (7681, [("auto", AUTO), ("rader-smooth4step", R.rader(7681)), ("bluestein-pow2", R.bluestein(7681))]),
     (112501, [("auto", AUTO), ("rader-smooth4step", R.rader(112501)), ("bluestein-pow2", R.bluestein(112501))]),
-    (65537, [("auto", AUTO), ("bluestein-pow2", R.bluestein(65537))]),
+    (65537, [("auto", AUTO), ("bluestein-pow2", R.bluestein(65537)), ("rader-cluster-8", R.rader(65537, 1, R.cluster(65536)))]),
+    (20011, [("auto", AUTO), ("bluestein-cluster-8", R.bluestein(20011, R.cluster(65536)))]),
+    (6007, [("auto", AUTO), ("bluestein-cluster-2", R.bluestein(6007, R.cluster(16384)))]),
     (4099, [("auto", AUTO), ("bluestein-pow2-16384", R.bluestein(4099, R.pow2(16384))), ("bluestein-smooth-8232", R.bluestein(4099, R.mixed_radix(84, 98)))]),
     (10000, [("auto", AUTO), ("smooth4step-100x100", R.mixed_radix(100, 100)), ("goodthomas-16x625", R.good_thomas(16, 625))]),
     (44100, [("auto", AUTO), ("smooth4step-210x210", R.mixed_radix(210, 210)), ("goodthomas-196x225", R.good_thomas(196, 225))]),
     (48000, [("auto", AUTO), ("goodthomas-128x375", R.good_thomas(128, 375))]),
     (1200, [("auto", AUTO), ("goodthomas-25x48", R.good_thomas(25, 48))]),
     (1000000, [("auto", AUTO)]),
+    (100000, [("auto", AUTO)]),
+    (16000, [("auto", AUTO)]), (62500, [("auto", AUTO)]), (200000, [("auto", AUTO)]), (390625, [("auto", AUTO)]),
+    (1000, [("auto", AUTO)]), (3600, [("auto", AUTO)]), (2187, [("auto", AUTO)]), (961, [("auto", AUTO)]),
+    # single pass on a thread-block cluster (DSMEM transpose) next to the default plan of the same length (f32)
+    (1 << 14, [("auto", AUTO), ("cluster-2", R.cluster(1 << 14))]),
+    (1 << 15, [("auto", AUTO), ("cluster-4", R.cluster(1 << 15))]),
+    (1 << 16, [("auto", AUTO), ("cluster-8", R.cluster(1 << 16))]),
+    (1 << 17, [("auto", AUTO), ("cluster-16", R.cluster(1 << 17))]),
 ]
 
 
@@ -53,7 +63,7 @@ def main():
         for n, alts in CASES:
             if only and n not in only:
                 continue
-            batch = max(1, (1 << 30) // (n * esz))
+            batch = max(1, (1 << (32 if n >= (1 << 14) and (n & (n - 1)) == 0 else 30)) // (n * esz))
             x = torch.empty(batch * n, dtype=tdt, device="cuda")
             torch.view_as_real(x).uniform_(0, 10)
             y = torch.empty_like(x)

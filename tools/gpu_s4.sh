@@ -1,0 +1,27 @@
+#!/bin/bash
+# session 4: full GPU suite, plan A/B (cluster convolution plans, 3-CTA smooth kernels, wider compiled tile set), bench, ncu evidence
+OUT=gpurun_out/s4
+mkdir -p $OUT
+export PYTHONPATH=$PWD:$PWD/tests
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.draw,memory.total --format=csv > $OUT/env.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log
+AB_PLANS_OUT=$OUT/ab_plans.json timeout 600 python tools/ab_plans.py 65537 20011 6007 617 1234 97 1009 2053 1200 1000 3600 2187 961 10000 16000 62500 200000 390625 44100 1000000 7681 > $OUT/ab_plans.txt 2>&1; echo "ab rc=$?"; cut -c1-200 $OUT/ab_plans.txt
+timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2>> $OUT/bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/s4/bench.json'))
+print("value",d["value"],"frac",d["roofline"]["frac"], "e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
+print("per_size", [(r["log2n"], r["frac"], r.get("frac_b2b")) for r in d["config"]["per_size"]])
+for r in d.get("other_configs") or []:
+    r=dict(r); r.pop("per_size",None); print(json.dumps(r)[:700])
+PY
+# ncu: launch list of one whole step with DRAM bytes (caches left alone), then --set full of the fused kernel at 2^20 and of the compiled composite passes
+timeout 600 /usr/local/cuda/bin/ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
+   -c 200 --csv --log-file $OUT/launches.csv python bench.py --profile --profile-cold --steps 1 > $OUT/ncu_list.log 2>&1
+python tools/launch_list_summary.py $OUT/launches.csv > $OUT/launch_list_summary.md 2>&1; gzip -9 -f $OUT/launches.csv; head -40 $OUT/launch_list_summary.md
+timeout 400 /usr/local/cuda/bin/ncu --set full --clock-control none --import-source on -k regex:run_fused -c 1 -o /tmp/full_fused python bench.py --profile --steps 1 --logs 20 > $OUT/ncu_fused.log 2>&1
+python tools/ncu_summary.py /tmp/full_fused.ncu-rep > $OUT/ncu_full_fused_1024x1024.md 2>&1
+timeout 300 /usr/local/cuda/bin/ncu --set full --clock-control none --import-source on -k regex:run_kernel -s 6 -c 2 -o /tmp/full_ctile python tools/ab_plans.py 1000000 > $OUT/ncu_ctile.log 2>&1
+python tools/ncu_summary.py /tmp/full_ctile.ncu-rep > $OUT/ncu_full_compiled_tiles_1000x1000.md 2>&1
+ls -la $OUT
