@@ -1772,9 +1772,11 @@ struct Builder {
         const uint64_t N = (uint64_t)L1 * L2;
         const C* full_tw = smooth_full_twiddles(pl, L1, L2);
         if (!full_tw) return false;
-        const int K = overlap_streams(4);
-        // K chunks in flight share ~48 MiB of L2; FFT indices of a launch stay below 2^31
-        uint64_t chunk = std::max<uint64_t>(1, (48ull << 20) / (N * sizeof(C)) / (uint64_t)K);
+        // chunks in flight share ~64 MiB of L2; a chunk should still fill the device about twice (a launch of 125 CTAs on 148 SMs is
+        // all ramp and tail), so long transforms use fewer streams; FFT indices of a launch stay below 2^31
+        const uint64_t fit = std::max<uint64_t>(1, (64ull << 20) / (N * sizeof(C)));
+        const int K = overlap_streams(fit >= 16 ? 4 : (fit >= 6 ? 2 : 1));
+        uint64_t chunk = std::max<uint64_t>(1, fit / (uint64_t)K);
         chunk = std::min<uint64_t>(chunk, ((1ull << 31) - 1) / std::max(L1, L2));
         pl.chunk = chunk;
         pl.work_bytes = [=](uint64_t batch) {
@@ -1853,8 +1855,9 @@ struct Builder {
         base.mult = upload(pl, mult);
         if (!base.mult) return false;
         // virtual transforms per CTA: a multiple of r0, both ping-pong buffers inside the budget, at most 64
-        // (inner lengths that fit the one-pass Smooth budget keep to it: 64 KiB per CTA leaves room for three CTAs per SM)
-        const uint32_t budget = (uint64_t)r0 * M <= SMOOTH_MAX ? SMOOTH_MAX : CONV_SMOOTH_MAX;
+        // (the instantiation without the prime butterflies fits three CTAs per SM when a CTA stays inside 64 KiB: measured +11..16 % at
+        //  97 / 1009; the 128-register one runs two CTAs either way and is faster with more transforms per CTA: 2053 0.077 vs 0.060)
+        const uint32_t budget = (RMAX <= 16 && (uint64_t)r0 * M <= SMOOTH_MAX) ? SMOOTH_MAX : CONV_SMOOTH_MAX;
         uint32_t F = std::max<uint32_t>(1, budget / M / r0) * r0;
         while (F > r0 && F > 64) F -= r0;
         base.f_per_cta = F;

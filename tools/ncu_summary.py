@@ -51,6 +51,23 @@ def main():
         for k, label in KEYS:
             if k in col:
                 print(f"| {label} (`{k}`) | {r[col[k]]} | {units[col[k]]} |")
+        # warp stall reasons, whatever this ncu version calls them: the eight largest "...issue_stalled_<reason>..." columns
+        stalls = []
+        for h, i in col.items():
+            m = re.search(r"issue_stalled_([a-z_]+?)(?:_per_|\.|$)", h)
+            if m and ("per_warp_active" in h or "ratio" in h):
+                try:
+                    stalls.append((float(r[i].replace(",", "")), m.group(1), h, units[i]))
+                except ValueError:
+                    pass
+        seen = set()
+        for v, reason, h, u in sorted(stalls, reverse=True):
+            if reason in seen:
+                continue
+            seen.add(reason)
+            if len(seen) > 8:
+                break
+            print(f"| stall {reason} (`{h}`) | {v:.3f} | {u} |")
         try:
             rd = float(r[col["dram__bytes_read.sum"]].replace(",", ""))
             wr = float(r[col["dram__bytes_write.sum"]].replace(",", ""))
