@@ -85,7 +85,8 @@ int b200fft_plan_destroy(b200fft_plan* plan);
  *                                                       fused); child = node of the inner FFT of length p - 1 (0 = AUTO)
  *   BLUESTEIN     BluesteinsAlgorithm                   child = node of the inner FFT, length M >= 2 len - 1 (0 = AUTO)
  *   CLUSTER       MixedRadix, on chip                   len = 2^14 .. 2^17 (f32): both passes inside one thread-block cluster, the
- *                                                       transpose through distributed shared memory (one pass over HBM) */
+ *                                                       transpose through distributed shared memory (one pass over HBM);
+ *                                                       a = 1: half tiles (4096 points per CTA, 2^14 .. 2^16) */
 enum {
     B200FFT_RECIPE_AUTO = 0,
     B200FFT_RECIPE_POW2 = 1,
@@ -104,6 +105,12 @@ typedef struct b200fft_recipe_node {
 } b200fft_recipe_node;
 int b200fft_plan_create_from_recipe(b200fft_plan** out, const b200fft_recipe_node* nodes, uint32_t n_nodes, int direction,
                                     int precision, int device);
+
+/* The decomposition a plan was built as, in the same node vocabulary (node 0 = root): a plan can be stored as data and rebuilt
+ * bit-identically with b200fft_plan_create_from_recipe -- plan serialisation for callers that cache plans across processes
+ * (the reference keeps its Recipe in memory only, src/plan.rs:134-226).  Returns the number of nodes (at most 2 today); writes
+ * min(cap, n) of them when `nodes` is not NULL. */
+int b200fft_plan_recipe(const b200fft_plan* plan, b200fft_recipe_node* nodes, uint32_t cap);
 
 uint64_t b200fft_plan_len(const b200fft_plan* plan);
 int b200fft_plan_direction(const b200fft_plan* plan);

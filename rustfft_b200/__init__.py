@@ -70,8 +70,19 @@ class Recipe:
         return cls(cls.POW2, n)
 
     @classmethod
-    def cluster(cls, n):
-        return cls(cls.CLUSTER, n)
+    def cluster(cls, n, half_tiles=False):
+        return cls(cls.CLUSTER, n, 1 if half_tiles else 0)
+
+    def to_dict(self):
+        """JSON-friendly form (plan serialisation): Recipe.from_dict(json.loads(json.dumps(r.to_dict()))) rebuilds the same plan."""
+        d = {"kind": self.kind, "len": self.len, "a": self.a, "b": self.b}
+        if self.inner is not None:
+            d["inner"] = self.inner.to_dict()
+        return d
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(d["kind"], d["len"], d.get("a", 0), d.get("b", 0), cls.from_dict(d["inner"]) if d.get("inner") else None)
 
     @classmethod
     def smooth(cls, n):
@@ -108,7 +119,8 @@ class Library:
     """A loaded C-ABI library (include/b200fft.h)."""
 
     SYMBOLS = [
-        "b200fft_device_count", "b200fft_plan_create", "b200fft_plan_create_from_recipe", "b200fft_plan_destroy", "b200fft_plan_len",
+        "b200fft_device_count", "b200fft_plan_create", "b200fft_plan_create_from_recipe", "b200fft_plan_recipe", "b200fft_plan_destroy",
+        "b200fft_plan_len",
         "b200fft_plan_direction", "b200fft_plan_precision", "b200fft_plan_scratch_len", "b200fft_plan_describe",
         "b200fft_plan_launches", "b200fft_exec_host_inplace", "b200fft_exec_host_outofplace", "b200fft_exec_device",
         "b200fft_workspace_bytes", "b200fft_exec_device_ws", "b200fft_last_error", "b200fft_version",
@@ -124,6 +136,7 @@ class Library:
         c.b200fft_device_count.argtypes = [ctypes.POINTER(i32)]
         c.b200fft_plan_create.argtypes = [ctypes.POINTER(vp), u64, i32, i32, i32]
         c.b200fft_plan_create_from_recipe.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(_RecipeNode), ctypes.c_uint32, i32, i32, i32]
+        c.b200fft_plan_recipe.argtypes = [vp, ctypes.POINTER(_RecipeNode), ctypes.c_uint32]
         c.b200fft_plan_destroy.argtypes = [vp]
         c.b200fft_plan_len.argtypes = [vp]
         c.b200fft_plan_len.restype = u64
@@ -217,6 +230,17 @@ class Fft:
         if rc < 0:
             self._lib.check(rc)
         return buf.value.decode()
+
+    def recipe(self) -> "Recipe":
+        """The decomposition this plan was built as (b200fft_plan_recipe): feed it to FftPlanner.plan_fft_with_recipe to rebuild it."""
+        arr = (_RecipeNode * 8)()
+        n = self._lib.c.b200fft_plan_recipe(self._h, arr, 8)
+        if n < 0:
+            self._lib.check(n)
+        rc = None
+        for i in range(n - 1, -1, -1):
+            rc = Recipe(arr[i].kind, arr[i].len, arr[i].a, arr[i].b, rc if arr[i].child else None)
+        return rc
 
     def launches(self, batch: int) -> int:
         return int(self._lib.c.b200fft_plan_launches(self._h, batch))

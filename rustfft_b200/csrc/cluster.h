@@ -44,7 +44,7 @@ struct ClusterKernel {
     static_assert(GA::NT == GB::NT, "both passes use the CTA's threads");
     static_assert(W * C == N2 && H * C == N1, "the cluster covers the transform");
     static_assert(GA::E == GB::E && H % GA::TP == 0, "a thread's slots of one exchange store go to one remote CTA");
-    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int MIN_BLOCKS = 512 / GA::NT;  // 128 registers per thread
     static constexpr int NPA = EA::NPHASE, NPB = EB::NPHASE;
     static constexpr int NPHASE = NPA + 2 + NPB;
     // CTA-local buffer: the engines' padded exchange buffers and the dense row-pass tile share it

@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -141,6 +142,11 @@ template <> struct FusedGeo<float, 1024> { using type = Geo<float, 1024, 32, 8, 
 B2_FUSED(2048, 4, 2, 32, 32)
 B2_FUSED(4096, 2, 4, 32, 32)
 static constexpr int FUSED_NG = 2, FUSED_NS = 3;  // consumer groups, shared-memory stages
+// half tiles for the cluster plans (4096 points, 128 threads per CTA: four CTAs per SM, twice the cluster size)
+template <int L> struct ClusterHalfGeo;
+template <> struct ClusterHalfGeo<128> { using type = Geo<float, 128, 32, 32, Radices<4, 32>>; };
+template <> struct ClusterHalfGeo<256> { using type = Geo<float, 256, 32, 16, Radices<8, 32>>; };
+template <> struct ClusterHalfGeo<512> { using type = Geo<float, 512, 32, 8, Radices<16, 32>>; };  // (only named by the full-tile 2^17 plan's type selection)
 
 // compiled tiles of COMPOSITE pass lengths (f32): the same CTA engine with radix-3 / 5 / 7 stages, for the two-pass plans of
 // 10000 = 100 x 100, 44100 = 196 x 225, 48000 = 128 x 375, 100000 = 100 x 1000 and 10^6 = 1000 x 1000 (the run-time-radix
@@ -241,6 +247,7 @@ struct b200fft_plan {
     std::mutex pipe_mutex;
     std::vector<b2::HostPipe*> pipes;
     std::vector<b200fft_recipe_node> recipe;  // b200fft_plan_create_from_recipe: the caller's decomposition (empty = plan here)
+    std::vector<b200fft_recipe_node> chosen;  // the decomposition that was built, in the same vocabulary (b200fft_plan_recipe)
     std::function<bool(const b2::ExecCtx&)> exec;
     std::function<uint64_t(uint64_t)> work_bytes = [](uint64_t) { return (uint64_t)0; };
     std::function<uint64_t(uint64_t)> launches = [](uint64_t) { return (uint64_t)0; };
@@ -252,6 +259,15 @@ struct b200fft_plan {
 };
 
 namespace b2 {
+
+// records what was built as a recipe (node 0 + optional inner node): b200fft_plan_recipe() hands it back, so a plan can be
+// stored as data and rebuilt with b200fft_plan_create_from_recipe()
+static void set_recipe(b200fft_plan& pl, uint32_t kind, uint64_t a = 0, uint64_t b = 0, uint32_t child_kind = 0, uint64_t child_len = 0,
+                       uint64_t child_a = 0, uint64_t child_b = 0) {
+    pl.chosen.clear();
+    pl.chosen.push_back(b200fft_recipe_node{kind, child_kind ? 1u : 0u, pl.len, a, b});
+    if (child_kind) pl.chosen.push_back(b200fft_recipe_node{child_kind, 0u, child_len, child_a, child_b});
+}
 
 template <class V>
 static const V* upload(b200fft_plan& pl, const std::vector<V>& host) {
@@ -496,7 +512,7 @@ template <> struct HasV1<float, 16384> { static constexpr bool direct = true, ti
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 // single-pass cluster plans (cluster.h), compiled in the same translation unit as the fused kernels
-bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN);
+bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half);
 // compiled composite tiles (b200fft_ctile32.cu)
 bool build_compiled_smooth_f32(b200fft_plan& pl, uint32_t a, uint32_t b);
 bool build_cluster_conv_f32(b200fft_plan& pl, uint64_t M, int mode);
@@ -563,6 +579,7 @@ struct Builder {
         };
         pl.launches = [](uint64_t) { return (uint64_t)1; };
         pl.desc = "Direct{" + std::to_string(L) + "}";
+        set_recipe(pl, B200FFT_RECIPE_POW2);
         return true;
     }
     template <int L>
@@ -972,11 +989,11 @@ struct Builder {
         }();
         return v;
     }
-    template <int L1, int L2, int CC, bool SW>
+    template <int L1, int L2, int CC, bool SW, bool HALF = false>
     static bool make_cluster_t(b200fft_plan& pl) {
         if constexpr (sizeof(T) == 4) {
-            using GA = typename FusedGeo<T, L1>::type;
-            using GB = typename FusedGeo<T, L2>::type;
+            using GA = typename std::conditional<HALF, typename ClusterHalfGeo<L1>::type, typename FusedGeo<T, L1>::type>::type;
+            using GB = typename std::conditional<HALF, typename ClusterHalfGeo<L2>::type, typename FusedGeo<T, L2>::type>::type;
             using KT = ClusterKernel<GA, GB, CC, SW>;
             static_assert(KT::SMEM_BYTES <= MAX_SMEM_PER_CTA, "cluster tile fits one CTA");
             const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2), lgN = lg1 + lg2;
@@ -1003,6 +1020,7 @@ struct Builder {
             };
             pl.launches = [=](uint64_t batch) { return (batch + ((1ull << 30) / CC) - 1) / ((1ull << 30) / CC); };
             pl.desc = "ClusterFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",cluster=" + std::to_string(CC) + "}";
+            set_recipe(pl, B200FFT_RECIPE_CLUSTER, HALF ? 1 : 0);
             return true;
         } else {
             (void)pl;
@@ -1062,6 +1080,7 @@ struct Builder {
             const std::string inner = "ClusterFourStep{" + std::to_string(L) + "x" + std::to_string(L) + ",cluster=" + std::to_string(CC) + "}";
             pl.desc = MODE == 0 ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + ",fused}"
                                 : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + ",fused}";
+            set_recipe(pl, MODE == 0 ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, MODE == 0 ? 1 : 0, 0, B200FFT_RECIPE_CLUSTER, M);
             return true;
         } else {
             (void)pl;
@@ -1093,8 +1112,16 @@ struct Builder {
         }();
         return v;
     }
-    static bool cluster_build_here(b200fft_plan& pl, uint32_t lgN) {
+    static bool cluster_build_here(b200fft_plan& pl, uint32_t lgN, bool half) {
         const bool sw = pl.direction != 0;
+        if (half) {  // 4096-point tiles, 128 threads: four CTAs per SM, twice the cluster size
+            switch (lgN) {
+                case 14: return sw ? make_cluster_t<128, 128, 4, true, true>(pl) : make_cluster_t<128, 128, 4, false, true>(pl);
+                case 15: return sw ? make_cluster_t<128, 256, 8, true, true>(pl) : make_cluster_t<128, 256, 8, false, true>(pl);
+                case 16: return sw ? make_cluster_t<256, 256, 16, true, true>(pl) : make_cluster_t<256, 256, 16, false, true>(pl);
+            }
+            return false;
+        }
         switch (lgN) {
             case 14: return sw ? make_cluster_t<128, 128, 2, true>(pl) : make_cluster_t<128, 128, 2, false>(pl);
             case 15: return sw ? make_cluster_t<128, 256, 4, true>(pl) : make_cluster_t<128, 256, 4, false>(pl);
@@ -1103,8 +1130,8 @@ struct Builder {
         }
         return false;
     }
-    static bool make_cluster(b200fft_plan& pl, uint32_t lgN) {
-        if constexpr (sizeof(T) == 4) return build_cluster_f32(pl, lgN);
+    static bool make_cluster(b200fft_plan& pl, uint32_t lgN, bool half = false) {
+        if constexpr (sizeof(T) == 4) return build_cluster_f32(pl, lgN, half);
         return false;
     }
 
@@ -1132,6 +1159,7 @@ struct Builder {
                 return ok;
             };
             pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + ",flow,ring=" + std::to_string(W) + "}";
+            set_recipe(pl, B200FFT_RECIPE_POW2);
             pl.chunk = W;
             return true;
         }
@@ -1221,6 +1249,7 @@ struct Builder {
             return ok;
         };
         pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + (fused ? ",fused,ring=" + std::to_string(fused_w) : std::string()) + "}";
+        set_recipe(pl, B200FFT_RECIPE_POW2);
         pl.chunk = fused ? fused_w : chunk;
         return true;
     }
@@ -1408,6 +1437,7 @@ struct Builder {
         const std::string inner = "FourStep{" + std::to_string(1u << t.lg1) + "x" + std::to_string(1u << t.lg2) + "}";
         pl.desc = rader ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + "}"
                         : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + "}";
+        set_recipe(pl, rader ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, rader ? 1 : 0, 0, B200FFT_RECIPE_POW2, M);
         return true;
     }
 
@@ -1485,6 +1515,7 @@ struct Builder {
         std::string rs;
         for (size_t s = 0; s < radices.size(); ++s) rs += (s ? "x" : "") + std::to_string(radices[s]);
         pl.desc = "Smooth{" + std::to_string(n) + "=" + rs + "}";
+        set_recipe(pl, B200FFT_RECIPE_SMOOTH);
         return true;
     }
     static bool make_smooth(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
@@ -1624,6 +1655,7 @@ struct Builder {
             return true;
         };
         pl.desc = std::string(variant == 1 ? "GoodThomas{" : "SmoothFourStep{") + std::to_string(N1) + "x" + std::to_string(N2) + "}";
+        set_recipe(pl, variant == 1 ? B200FFT_RECIPE_GOOD_THOMAS : B200FFT_RECIPE_MIXED_RADIX, N1, N2);
         return true;
     }
     static bool make_smooth_four_step(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
@@ -1795,6 +1827,7 @@ struct Builder {
             });
         };
         pl.desc = "SmoothFourStep{" + std::to_string(L1) + "x" + std::to_string(L2) + ",compiled}";
+        set_recipe(pl, B200FFT_RECIPE_MIXED_RADIX, L1, L2);
         return true;
     }
     static bool make_compiled_smooth(b200fft_plan& pl, uint32_t a, uint32_t b) {
@@ -1879,6 +1912,7 @@ struct Builder {
         } else {
             pl.desc = "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + ",fused}";
         }
+        set_recipe(pl, mode == 0 ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, mode == 0 ? r0 : 0, 0, B200FFT_RECIPE_SMOOTH, M);
         return true;
     }
     static bool make_smooth_conv(b200fft_plan& pl, int mode, uint32_t r0, uint32_t pM) {
@@ -1968,6 +2002,7 @@ struct Builder {
         const std::string inner = "SmoothFourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + "}";
         pl.desc = rader ? "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(groot) + ",inner=" + inner + "}"
                         : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + "}";
+        set_recipe(pl, rader ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, rader ? 1 : 0, 0, B200FFT_RECIPE_MIXED_RADIX, M, N1, N2);
         return true;
     }
     static bool make_smooth_big_conv(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
@@ -2014,6 +2049,7 @@ struct Builder {
         };
         pl.launches = [](uint64_t) { return (uint64_t)1; };
         pl.desc = "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",fused}";
+        set_recipe(pl, B200FFT_RECIPE_BLUESTEIN, 0, 0, B200FFT_RECIPE_POW2, M);
         return true;
     }
     template <int M>
@@ -2086,6 +2122,7 @@ struct Builder {
         };
         pl.launches = [](uint64_t) { return (uint64_t)1; };
         pl.desc = "Rader{n=" + std::to_string(n) + ",g=" + std::to_string(g) + ",fused}";
+        set_recipe(pl, B200FFT_RECIPE_RADER, 1, 0, B200FFT_RECIPE_POW2, M);
         return true;
     }
     template <int M>
@@ -2268,7 +2305,8 @@ struct Builder {
             }
             case B200FFT_RECIPE_CLUSTER: {
                 if (sizeof(T) != 4 || !hm::is_pow2(n) || n < (1u << 14) || n > (1u << 17)) return unsupported("CLUSTER plans exist for f32, 2^14 .. 2^17");
-                ok = make_cluster(pl, hm::ilog2(n));
+                if (r.a == 1 && n > (1u << 16)) return unsupported("half-tile CLUSTER plans exist for 2^14 .. 2^16");
+                ok = make_cluster(pl, hm::ilog2(n), r.a == 1);
                 break;
             }
             default:
@@ -2287,6 +2325,7 @@ struct Builder {
                 return rt::d2d_async(c.out, c.in, c.batch * n * sizeof(C), c.stream);
             };
             pl.desc = "Identity{" + std::to_string(n) + "}";
+            set_recipe(pl, B200FFT_RECIPE_AUTO);
             return B200FFT_OK;
         }
         // lengths this build cannot plan are rejected BEFORE any factoring / primality work (a prime near 2^62 would otherwise
@@ -2373,7 +2412,7 @@ int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here(pl, kind, a, b); }
 #endif
 #if defined(B2_PART_FUSED32)
-bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN) { return Builder<float>::cluster_build_here(pl, lgN); }
+bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half) { return Builder<float>::cluster_build_here(pl, lgN, half); }
 bool build_cluster_conv_f32(b200fft_plan& pl, uint64_t M, int mode) { return Builder<float>::cluster_conv_build_here(pl, M, mode); }
 bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, const void* full_tw, FusedFn& fn, uint32_t& W) {
     return Builder<float>::fused_build_here(pl, L1, L2, lgN, (const cx<float>*)full_tw, fn, W);
@@ -2792,6 +2831,14 @@ int b200fft_plan_destroy(b200fft_plan* plan) {
     b2::rt::set_device(plan->device);
     delete plan;
     return B200FFT_OK;
+}
+
+int b200fft_plan_recipe(const b200fft_plan* plan, b200fft_recipe_node* nodes, uint32_t cap) {
+    if (!plan) return b2::fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    const uint32_t n = (uint32_t)plan->chosen.size();
+    if (nodes)
+        for (uint32_t i = 0; i < n && i < cap; ++i) nodes[i] = plan->chosen[i];
+    return (int)n;
 }
 
 uint64_t b200fft_plan_len(const b200fft_plan* plan) { return plan ? plan->len : 0; }

@@ -168,6 +168,11 @@ def check_cluster_plans(planner, dtype):
         assert rel_l2(a, b) < 1e-6
     with pytest.raises(rb.FftError, match="CLUSTER"):
         planner.plan_fft_with_recipe(R.cluster(1 << 18), DIRS[0])
+    for lg, c in [(14, 4), (15, 8), (16, 16)]:  # half tiles: 4096 points and 128 threads per CTA, twice the cluster size
+        n = 1 << lg
+        for d in DIRS:
+            f = check_fft_algorithm(planner, n, d, dtype, control_kind=oracle.PLANNER, chunks=3, recipe=R.cluster(n, half_tiles=True))
+            assert f.describe() == "ClusterFourStep{%dx%d,cluster=%d}" % (1 << (lg // 2), 1 << (lg - lg // 2), c), f.describe()
     # the whole Rader / Bluestein algorithm inside one cluster pass (BASELINE config 4: n = 65537)
     for rc, want in [(R.rader(65537, 1, R.cluster(65536)), "Rader{n=65537,g=3,inner=ClusterFourStep{256x256,cluster=8},fused}"),
                      (R.bluestein(20011, R.cluster(65536)), "Bluestein{n=20011,M=65536,inner=ClusterFourStep{256x256,cluster=8},fused}"),
@@ -178,5 +183,25 @@ def check_cluster_plans(planner, dtype):
             assert f.describe() == want, f.describe()
 
 
-ALL = [check_cluster_plans, check_rader_primes_below_100, check_default_prime_rule, check_mixed_radix_rader, check_overflow_primes, check_good_thomas_small_pairs,
+def check_plan_serialisation(planner, dtype):
+    """b200fft_plan_recipe: the decomposition a plan was built as comes back as data (JSON-able), and b200fft_plan_create_from_recipe rebuilds
+    the same plan from it -- same description, bit-identical results (plan caching across processes)."""
+    import json
+
+    from util import signal
+
+    for n in [8, 1024, 1 << 15, 1000, 5000, 10000, 44100, 617, 1234, 97, 257, 65537, 719, 4099]:
+        for d in DIRS:
+            f = planner.plan_fft(n, d)
+            rc = R.from_dict(json.loads(json.dumps(f.recipe().to_dict())))
+            g = planner.plan_fft_with_recipe(rc, d)
+            assert g.describe() == f.describe() and g.len() == n, (n, f.describe(), g.describe())
+            x = signal(3 * n, dtype, seed=n)
+            a, b = x.copy(), x.copy()
+            f.process(a)
+            g.process(b)
+            assert np.array_equal(a, b), n
+
+
+ALL = [check_plan_serialisation, check_cluster_plans, check_rader_primes_below_100, check_default_prime_rule, check_mixed_radix_rader, check_overflow_primes, check_good_thomas_small_pairs,
        check_good_thomas_large, check_bluestein_inner_lengths, check_recipes_of_existing_kinds]

@@ -46,9 +46,9 @@ CASES = [
     (16000, [("auto", AUTO)]), (62500, [("auto", AUTO)]), (200000, [("auto", AUTO)]), (390625, [("auto", AUTO)]),
     (1000, [("auto", AUTO)]), (3600, [("auto", AUTO)]), (2187, [("auto", AUTO)]), (961, [("auto", AUTO)]),
     # single pass on a thread-block cluster (DSMEM transpose) next to the default plan of the same length (f32)
-    (1 << 14, [("auto", AUTO), ("cluster-2", R.cluster(1 << 14))]),
-    (1 << 15, [("auto", AUTO), ("cluster-4", R.cluster(1 << 15))]),
-    (1 << 16, [("auto", AUTO), ("cluster-8", R.cluster(1 << 16))]),
+    (1 << 14, [("auto", AUTO), ("cluster-2", R.cluster(1 << 14)), ("cluster-4-half-tiles", R.cluster(1 << 14, True))]),
+    (1 << 15, [("auto", AUTO), ("cluster-4", R.cluster(1 << 15)), ("cluster-8-half-tiles", R.cluster(1 << 15, True))]),
+    (1 << 16, [("auto", AUTO), ("cluster-8", R.cluster(1 << 16)), ("cluster-16-half-tiles", R.cluster(1 << 16, True))]),
     (1 << 17, [("auto", AUTO), ("cluster-16", R.cluster(1 << 17))]),
 ]
 
