@@ -40,9 +40,11 @@ inline int fail(int code, const std::string& msg) {
 // which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
 // harness defines none and gets everything)
 #if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64) && \
-    !defined(B2_PART_FUSED32) && !defined(B2_PART_CTILE32)
+    !defined(B2_PART_FUSED32) && !defined(B2_PART_CTILE32) && !defined(B2_PART_SMOOTH32S) && !defined(B2_PART_SMOOTH64S)
 #define B2_PART_FUSED32 1
 #define B2_PART_CTILE32 1
+#define B2_PART_SMOOTH32S 1
+#define B2_PART_SMOOTH64S 1
 #define B2_PART_CABI 1
 #define B2_PART_F32 1
 #define B2_PART_F64 1
@@ -511,6 +513,8 @@ template <> struct HasV1<float, 16384> { static constexpr bool direct = true, ti
 // kind 0: one-pass Smooth plan of pl.len;  kind 1: SmoothFourStep{a x b}
 bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+bool build_smooth_small_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+bool build_smooth_small_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 // single-pass cluster plans (cluster.h), compiled in the same translation unit as the fused kernels
 bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half);
 // compiled composite tiles (b200fft_ctile32.cu)
@@ -523,23 +527,38 @@ bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, c
 template <typename T>
 struct Builder {
     typedef cx<T> C;
+    // the run-time-radix kernels exist in two instantiations -- with the prime butterflies 11..31 (128 registers, 2 CTAs per SM) and
+    // without them (3 CTAs per SM) -- each in translation units of its own; which one a plan needs is decided here
+    static bool smooth_kind_is_small(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+        std::vector<uint32_t> r;
+        switch (kind) {
+            case 0: return smooth_factor(pl.len, r) && max_radix(r) <= 16;
+            case 2: return smooth_factor((uint64_t)b - 1, r) && max_radix(r) <= 16;
+            case 3: return smooth_factor(a, r) && max_radix(r) <= 16;
+            default: return small_radices_only(a, b);
+        }
+    }
     static bool smooth_dispatch(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+        const bool small = smooth_kind_is_small(pl, kind, a, b);
         if constexpr (sizeof(T) == 4)
-            return build_smooth_f32(pl, kind, a, b);
+            return small ? build_smooth_small_f32(pl, kind, a, b) : build_smooth_f32(pl, kind, a, b);
         else
-            return build_smooth_f64(pl, kind, a, b);
+            return small ? build_smooth_small_f64(pl, kind, a, b) : build_smooth_f64(pl, kind, a, b);
     }
     // kind 0: Smooth; 1: SmoothFourStep{a x b}; 2: one-pass Rader, outer radix a, prime b; 3: one-pass Bluestein, inner M = a;
     //      4: GoodThomas{a x b}; 5: Rader over SmoothFourStep{a x b}; 6: Bluestein over SmoothFourStep{a x b}
+    template <int RMAX>
     static bool smooth_build_here(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
-        if (kind == 1) return make_smooth_four_step(pl, a, b, 0);
-        if (kind == 4) return make_smooth_four_step(pl, a, b, 1);
-        if (kind == 2) return make_smooth_conv(pl, 0, a, b);
-        if (kind == 3) return make_smooth_conv(pl, 1, 1, a);
-        if (kind == 5) return make_smooth_big_conv(pl, a, b, true);
-        if (kind == 6) return make_smooth_big_conv(pl, a, b, false);
+        const bool sw = pl.direction != 0;
+        if (kind == 1 || kind == 4)
+            return sw ? make_smooth_four_step_t<true, RMAX>(pl, a, b, kind == 4 ? 1 : 0) : make_smooth_four_step_t<false, RMAX>(pl, a, b, kind == 4 ? 1 : 0);
+        if (kind == 2) return sw ? make_smooth_conv_t<true, RMAX>(pl, 0, a, b) : make_smooth_conv_t<false, RMAX>(pl, 0, a, b);
+        if (kind == 3) return sw ? make_smooth_conv_t<true, RMAX>(pl, 1, 1, a) : make_smooth_conv_t<false, RMAX>(pl, 1, 1, a);
+        if (kind == 5 || kind == 6)
+            return sw ? make_smooth_big_conv_t<true, RMAX>(pl, a, b, kind == 5) : make_smooth_big_conv_t<false, RMAX>(pl, a, b, kind == 5);
         std::vector<uint32_t> radices;
-        return smooth_factor(pl.len, radices) && make_smooth(pl, radices);
+        if (!smooth_factor(pl.len, radices)) return false;
+        return sw ? make_smooth_t<true, RMAX>(pl, radices) : make_smooth_t<false, RMAX>(pl, radices);
     }
 
     // ---------------- Direct ----------------
@@ -1472,9 +1491,6 @@ struct Builder {
     }
     template <bool SW, int RMAX = 31>
     static bool make_smooth_t(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
-        if constexpr (RMAX > 16) {
-            if (max_radix(radices) <= 16) return make_smooth_t<SW, 16>(pl, radices);  // the 3-CTA-per-SM instantiation
-        }
         using KT = SmoothKernel<T, SW, RMAX>;
         const uint32_t n = (uint32_t)pl.len;
         typename KT::Params base;
@@ -1517,9 +1533,6 @@ struct Builder {
         pl.desc = "Smooth{" + std::to_string(n) + "=" + rs + "}";
         set_recipe(pl, B200FFT_RECIPE_SMOOTH);
         return true;
-    }
-    static bool make_smooth(b200fft_plan& pl, const std::vector<uint32_t>& radices) {
-        return pl.direction ? make_smooth_t<true>(pl, radices) : make_smooth_t<false>(pl, radices);
     }
 
     // ---------------- SmoothFourStep: composite N = N1 * N2 above SMOOTH_MAX, every prime factor <= 31 ----------------
@@ -1604,9 +1617,6 @@ struct Builder {
     }
     template <bool SW, int RMAX = 31>
     static bool make_smooth_four_step_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
-        if constexpr (RMAX > 16) {
-            if (small_radices_only(N1, N2)) return make_smooth_four_step_t<SW, 16>(pl, N1, N2, variant);
-        }
         using KA = SmoothPassKernel<T, SW, 1, RMAX>;
         using KB = SmoothPassKernel<T, SW, 2, RMAX>;
         const uint64_t N = (uint64_t)N1 * N2;
@@ -1657,9 +1667,6 @@ struct Builder {
         pl.desc = std::string(variant == 1 ? "GoodThomas{" : "SmoothFourStep{") + std::to_string(N1) + "x" + std::to_string(N2) + "}";
         set_recipe(pl, variant == 1 ? B200FFT_RECIPE_GOOD_THOMAS : B200FFT_RECIPE_MIXED_RADIX, N1, N2);
         return true;
-    }
-    static bool make_smooth_four_step(b200fft_plan& pl, uint32_t N1, uint32_t N2, int variant) {
-        return pl.direction ? make_smooth_four_step_t<true>(pl, N1, N2, variant) : make_smooth_four_step_t<false>(pl, N1, N2, variant);
     }
     // coprime split N = N1 * N2 for GoodThomas: both factors <= SMOOTH_MAX and smooth, as balanced as possible
     static bool coprime_split(uint64_t n, uint32_t& n1, uint32_t& n2) {
@@ -1850,9 +1857,6 @@ struct Builder {
         const uint32_t M = mode == 0 ? pM - 1 : pM;
         std::vector<uint32_t> radices;
         if (!smooth_factor(M, radices) || (uint64_t)r0 * M > CONV_SMOOTH_MAX) return false;
-        if constexpr (RMAX > 16) {
-            if (max_radix(radices) <= 16) return make_smooth_conv_t<SW, 16>(pl, mode, r0, pM);
-        }
         typename KT::Params base;
         if (!fill_smooth_pass<KT>(pl, base, M, radices)) return false;
         base.n = n;
@@ -1915,18 +1919,12 @@ struct Builder {
         set_recipe(pl, mode == 0 ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, mode == 0 ? r0 : 0, 0, B200FFT_RECIPE_SMOOTH, M);
         return true;
     }
-    static bool make_smooth_conv(b200fft_plan& pl, int mode, uint32_t r0, uint32_t pM) {
-        return pl.direction ? make_smooth_conv_t<true>(pl, mode, r0, pM) : make_smooth_conv_t<false>(pl, mode, r0, pM);
-    }
 
     // ---------------- large Rader / Bluestein over a smooth two-pass inner FFT of M = N1 * N2 ----------------
     // the four launches of make_big_conv (A1 gather|chirp-pad, B1 x mult + conj (+ DC), A2 plain, B2 conj + scatter | conj x chirp)
     // with the run-time-radix passes: any "easy" prime (p - 1 smooth) above the one-pass limit, Bluestein with the smallest smooth M
     template <bool SW, int RMAX = 31>
     static bool make_smooth_big_conv_t(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
-        if constexpr (RMAX > 16) {
-            if (small_radices_only(N1, N2)) return make_smooth_big_conv_t<SW, 16>(pl, N1, N2, rader);
-        }
         using KA = SmoothPassKernel<T, SW, 1, RMAX>;
         using KA2 = SmoothPassKernel<T, false, 1, RMAX>;
         using KB = SmoothPassKernel<T, SW, 2, RMAX>;
@@ -2004,9 +2002,6 @@ struct Builder {
                         : "Bluestein{n=" + std::to_string(n) + ",M=" + std::to_string(M) + ",inner=" + inner + "}";
         set_recipe(pl, rader ? B200FFT_RECIPE_RADER : B200FFT_RECIPE_BLUESTEIN, rader ? 1 : 0, 0, B200FFT_RECIPE_MIXED_RADIX, M, N1, N2);
         return true;
-    }
-    static bool make_smooth_big_conv(b200fft_plan& pl, uint32_t N1, uint32_t N2, bool rader) {
-        return pl.direction ? make_smooth_big_conv_t<true>(pl, N1, N2, rader) : make_smooth_big_conv_t<false>(pl, N1, N2, rader);
     }
 
     // ---------------- Bluestein (fused) ----------------
@@ -2409,7 +2404,10 @@ int build_plan_f32(b200fft_plan& pl) { return Builder<float>::build(pl); }
 int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
 #endif
 #if defined(B2_PART_SMOOTH32)
-bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here(pl, kind, a, b); }
+bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here<31>(pl, kind, a, b); }
+#endif
+#if defined(B2_PART_SMOOTH32S)
+bool build_smooth_small_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here<16>(pl, kind, a, b); }
 #endif
 #if defined(B2_PART_FUSED32)
 bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half) { return Builder<float>::cluster_build_here(pl, lgN, half); }
@@ -2422,7 +2420,10 @@ bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, c
 bool build_compiled_smooth_f32(b200fft_plan& pl, uint32_t a, uint32_t b) { return Builder<float>::compiled_smooth_build_here(pl, a, b); }
 #endif
 #if defined(B2_PART_SMOOTH64)
-bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here(pl, kind, a, b); }
+bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here<31>(pl, kind, a, b); }
+#endif
+#if defined(B2_PART_SMOOTH64S)
+bool build_smooth_small_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here<16>(pl, kind, a, b); }
 #endif
 
 }  // namespace b2
