@@ -139,6 +139,19 @@ uint64_t b200fft_workspace_bytes(const b200fft_plan* plan, uint64_t batch);
 int b200fft_exec_device_ws(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch,
                            void* cuda_stream, void* d_workspace, uint64_t workspace_bytes);
 
+/* Real-input / real-output transforms of even length on top of the complex plans (what the `realfft` crate adds above
+ * RustFFT's Fft trait; RustFFT itself has none).  forward: batch * len reals -> batch * (len/2 + 1) complex (the non-redundant half of the
+ * spectrum); inverse: the reverse, unnormalised (inverse(forward(x)) = len * x).  Device-resident entry points (asynchronous on the stream)
+ * and synchronous host ones (plain copies in and out, not pipelined). */
+typedef struct b200fft_real_plan b200fft_real_plan;
+int b200fft_real_plan_create(b200fft_real_plan** out, uint64_t len, int precision, int device);
+int b200fft_real_plan_destroy(b200fft_real_plan* plan);
+uint64_t b200fft_real_workspace_bytes(const b200fft_real_plan* plan, uint64_t batch);
+int b200fft_real_forward_device(const b200fft_real_plan* plan, const void* d_real_in, void* d_complex_out, uint64_t batch, void* cuda_stream);
+int b200fft_real_inverse_device(const b200fft_real_plan* plan, const void* d_complex_in, void* d_real_out, uint64_t batch, void* cuda_stream);
+int b200fft_real_forward_host(const b200fft_real_plan* plan, const void* real_in, void* complex_out, uint64_t batch);
+int b200fft_real_inverse_host(const b200fft_real_plan* plan, const void* complex_in, void* real_out, uint64_t batch);
+
 /* Message of the last failing call on this thread ("" if none). */
 const char* b200fft_last_error(void);
 /* Library build string: "b200fft <version> sm_100a" */

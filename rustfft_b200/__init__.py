@@ -26,7 +26,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "Recipe", "default_library", "shard_range"]
+__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "Recipe", "RealFftPlanner", "RealFft", "default_library", "shard_range"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200FFT_LIB: load another build of the same C ABI (A/B measurements of kernel variants; tools/ab_two_pass.py)
@@ -124,6 +124,8 @@ class Library:
         "b200fft_plan_direction", "b200fft_plan_precision", "b200fft_plan_scratch_len", "b200fft_plan_describe",
         "b200fft_plan_launches", "b200fft_exec_host_inplace", "b200fft_exec_host_outofplace", "b200fft_exec_device",
         "b200fft_workspace_bytes", "b200fft_exec_device_ws", "b200fft_last_error", "b200fft_version",
+        "b200fft_real_plan_create", "b200fft_real_plan_destroy", "b200fft_real_workspace_bytes", "b200fft_real_forward_device",
+        "b200fft_real_inverse_device", "b200fft_real_forward_host", "b200fft_real_inverse_host",
     ]
 
     def __init__(self, path: str = DEFAULT_LIB_PATH):
@@ -155,6 +157,14 @@ class Library:
         c.b200fft_exec_device_ws.argtypes = [vp, vp, vp, u64, vp, vp, u64]
         c.b200fft_last_error.restype = ctypes.c_char_p
         c.b200fft_version.restype = ctypes.c_char_p
+        c.b200fft_real_plan_create.argtypes = [ctypes.POINTER(vp), u64, i32, i32]
+        c.b200fft_real_plan_destroy.argtypes = [vp]
+        c.b200fft_real_workspace_bytes.argtypes = [vp, u64]
+        c.b200fft_real_workspace_bytes.restype = u64
+        c.b200fft_real_forward_device.argtypes = [vp, vp, vp, u64, vp]
+        c.b200fft_real_inverse_device.argtypes = [vp, vp, vp, u64, vp]
+        c.b200fft_real_forward_host.argtypes = [vp, vp, vp, u64]
+        c.b200fft_real_inverse_host.argtypes = [vp, vp, vp, u64]
 
     def device_count(self) -> int:
         n = ctypes.c_int(0)
@@ -383,6 +393,90 @@ class FftPlanner:
 
     def plan_fft_inverse(self, len: int) -> Fft:
         return self.plan_fft(len, FftDirection.Inverse)
+
+
+class RealFft:
+    """Real-to-complex / complex-to-real transforms of one even length (the shape of the `realfft` crate's RealToComplex /
+    ComplexToReal on top of RustFFT's Fft; SURVEY 8(f).4).  forward: batch * len reals -> batch * (len/2 + 1) complex;
+    inverse: the reverse, unnormalised (inverse(forward(x)) == len * x).  numpy arrays go through the synchronous host entry
+    points, torch CUDA tensors through the device ones (asynchronous on torch's current stream)."""
+
+    def __init__(self, lib: Library, length: int, precision: int, device: int):
+        self._lib, self._len, self._precision, self.device = lib, int(length), precision, device
+        self._h = ctypes.c_void_p()
+        lib.check(lib.c.b200fft_real_plan_create(ctypes.byref(self._h), self._len, precision, device))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.c.b200fft_real_plan_destroy(h)
+            except Exception:
+                pass
+
+    def len(self) -> int:
+        return self._len
+
+    def complex_len(self) -> int:
+        return self._len // 2 + 1
+
+    def _dtypes(self):
+        return (np.float32, np.complex64) if self._precision == F32 else (np.float64, np.complex128)
+
+    def _run(self, inverse: bool, src, dst):
+        rdt, cdt = self._dtypes()
+        n, h = self._len, self._len // 2 + 1
+        sdt, ddt, sper, dper = (cdt, rdt, h, n) if inverse else (rdt, cdt, n, h)
+        if isinstance(src, np.ndarray):
+            if src.dtype != sdt or dst.dtype != ddt or not src.flags.c_contiguous or not dst.flags.c_contiguous or not dst.flags.writeable:
+                raise TypeError(f"RealFft wants contiguous {np.dtype(sdt)} input and writable {np.dtype(ddt)} output")
+            if src.size % sper or dst.size != src.size // sper * dper:
+                raise FftError(-6, f"RealFft: input holds {src.size} elements, output {dst.size}: expected batch * {sper} and batch * {dper}")
+            fn = self._lib.c.b200fft_real_inverse_host if inverse else self._lib.c.b200fft_real_forward_host
+            self._lib.check(fn(self._h, src.ctypes.data, dst.ctypes.data, src.size // sper))
+            return dst
+        import torch
+
+        tmap = {np.float32: torch.float32, np.float64: torch.float64, np.complex64: torch.complex64, np.complex128: torch.complex128}
+        if src.dtype != tmap[sdt] or dst.dtype != tmap[ddt] or not src.is_cuda or not dst.is_cuda or not src.is_contiguous() or not dst.is_contiguous():
+            raise TypeError("RealFft wants contiguous CUDA tensors of the plan's real / complex dtypes")
+        if src.numel() % sper or dst.numel() != src.numel() // sper * dper:
+            raise FftError(-6, f"RealFft: input holds {src.numel()} elements, output {dst.numel()}: expected batch * {sper} and batch * {dper}")
+        fn = self._lib.c.b200fft_real_inverse_device if inverse else self._lib.c.b200fft_real_forward_device
+        self._lib.check(fn(self._h, src.data_ptr(), dst.data_ptr(), src.numel() // sper, torch.cuda.current_stream(src.device).cuda_stream))
+        return dst
+
+    def forward(self, real_in, complex_out):
+        return self._run(False, real_in, complex_out)
+
+    def inverse(self, complex_in, real_out):
+        return self._run(True, complex_in, real_out)
+
+
+class RealFftPlanner:
+    """Plans RealFft instances (cached per length), like realfft::RealFftPlanner over rustfft::FftPlanner."""
+
+    def __init__(self, dtype=np.float32, device: int = 0, lib: Optional[Library] = None):
+        dt = np.dtype(dtype)
+        if dt in (np.dtype(np.float32), np.dtype(np.complex64)):
+            self._precision = F32
+        elif dt in (np.dtype(np.float64), np.dtype(np.complex128)):
+            self._precision = F64
+        else:
+            raise TypeError("RealFftPlanner accelerates f32 and f64 only")
+        self._lib = lib if lib is not None else default_library()
+        if self._lib.device_count() <= 0:
+            raise FftError(-2, "no sm_100 CUDA device is visible (there is no CPU fallback)")
+        self.device = device
+        self._cache: Dict[int, RealFft] = {}
+        self._lock = threading.Lock()
+
+    def plan_fft(self, len: int) -> RealFft:
+        with self._lock:
+            f = self._cache.get(int(len))
+            if f is None:
+                f = self._cache[int(len)] = RealFft(self._lib, int(len), self._precision, self.device)
+            return f
 
 
 def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:

@@ -27,6 +27,7 @@
 #include "host_math.h"
 #include "fused.h"
 #include "cluster.h"
+#include "real.h"
 
 namespace b2 {
 
@@ -2880,6 +2881,141 @@ uint64_t b200fft_workspace_bytes(const b200fft_plan* plan, uint64_t batch) { ret
 int b200fft_exec_device_ws(const b200fft_plan* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream,
                            void* d_workspace, uint64_t workspace_bytes) {
     return b2::exec_device_impl(plan, d_in, d_out, batch, (b2::rt::stream_t)cuda_stream, d_workspace, workspace_bytes, true);
+}
+
+}  // extern "C"
+
+// ---- real-input / real-output wrappers (real.h) ----------------------------------------------------------------------------
+struct b200fft_real_plan {
+    uint64_t len = 0, M = 0;
+    int precision = 0, device = 0;
+    b200fft_plan* fwd = nullptr;  // M-point complex plans
+    b200fft_plan* inv = nullptr;
+    void* tw = nullptr;           // W_len^k, k = 0 .. M/2
+    ~b200fft_real_plan() {
+        if (fwd) b200fft_plan_destroy(fwd);
+        if (inv) b200fft_plan_destroy(inv);
+        if (tw) b2::rt::dfree(tw);
+    }
+};
+
+namespace b2 {
+template <typename T>
+static bool real_pack_launch(const b200fft_real_plan* rp, int dir, const void* in, void* out, uint64_t batch, rt::stream_t s) {
+    const uint32_t h = (uint32_t)(rp->M / 2 + 1);
+    if (dir == 0) {
+        typename RealPackKernel<T, 0>::Params p{(const cx<T>*)in, (cx<T>*)out, (const cx<T>*)rp->tw, batch * h, (uint32_t)rp->M, make_fastdiv(h)};
+        return rt::launch<RealPackKernel<T, 0>>(p, (p.n_pairs + 255) / 256, s);
+    }
+    typename RealPackKernel<T, 1>::Params p{(const cx<T>*)in, (cx<T>*)out, (const cx<T>*)rp->tw, batch * h, (uint32_t)rp->M, make_fastdiv(h)};
+    return rt::launch<RealPackKernel<T, 1>>(p, (p.n_pairs + 255) / 256, s);
+}
+// forward: real (as M complex) --FFT_M--> work --unpack--> out;   inverse: in --pack--> work --IFFT_M--> real out (as M complex)
+static int real_exec_device(const b200fft_real_plan* rp, bool inverse, const void* d_in, void* d_out, uint64_t batch, rt::stream_t stream) {
+    if (!rp || !d_in || !d_out) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    if (batch == 0) return B200FFT_OK;
+    if (batch * (rp->M / 2 + 1) >= (1ull << 31)) return fail(B200FFT_ERR_UNSUPPORTED, "real transforms: batch * (len/4 + 1) must stay below 2^31 per call");
+    rt::DeviceGuard guard(rp->device);
+    if (!guard.ok) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    const uint64_t esz = rp->precision == B200FFT_F32 ? 8 : 16;
+    const uint64_t zbytes = (batch * rp->M * esz + 255) / 256 * 256;
+    const b200fft_plan* cp = inverse ? rp->inv : rp->fwd;
+    const uint64_t inner = cp->work_bytes(batch);
+    char* work = (char*)rt::malloc_async(zbytes + inner + 256, stream);
+    if (!work) return fail(B200FFT_ERR_CUDA, "workspace allocation failed: " + rt::last_error());
+    void* z = work;
+    void* iw = inner ? work + zbytes : nullptr;
+    int rc = B200FFT_OK;
+    bool ok = true;
+    if (!inverse) {
+        rc = exec_device_impl(cp, d_in, z, batch, stream, iw, inner, inner != 0);
+        if (rc == B200FFT_OK) ok = rp->precision == B200FFT_F32 ? real_pack_launch<float>(rp, 0, z, d_out, batch, stream) : real_pack_launch<double>(rp, 0, z, d_out, batch, stream);
+    } else {
+        ok = rp->precision == B200FFT_F32 ? real_pack_launch<float>(rp, 1, d_in, z, batch, stream) : real_pack_launch<double>(rp, 1, d_in, z, batch, stream);
+        if (ok) rc = exec_device_impl(cp, z, d_out, batch, stream, iw, inner, inner != 0);
+    }
+    rt::free_async(work, stream);
+    if (rc != B200FFT_OK) return rc;
+    if (!ok) return fail(B200FFT_ERR_CUDA, "kernel launch failed: " + rt::last_error());
+    return B200FFT_OK;
+}
+static int real_exec_host(const b200fft_real_plan* rp, bool inverse, const void* in, void* out, uint64_t batch) {
+    if (!rp || !in || !out) return fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    if (batch == 0) return B200FFT_OK;
+    rt::DeviceGuard guard(rp->device);
+    if (!guard.ok) return fail(B200FFT_ERR_CUDA, rt::last_error());
+    const uint64_t esz = rp->precision == B200FFT_F32 ? 8 : 16;
+    const uint64_t rbytes = batch * rp->M * esz, cbytes = batch * (rp->M + 1) * esz;
+    const uint64_t ib = inverse ? cbytes : rbytes, ob = inverse ? rbytes : cbytes;
+    void* d_in = rt::dmalloc(ib);
+    void* d_out = rt::dmalloc(ob);
+    rt::stream_t s = rt::stream_create();
+    int rc = (d_in && d_out && s) ? B200FFT_OK : fail(B200FFT_ERR_CUDA, "staging allocation failed: " + rt::last_error());
+    if (rc == B200FFT_OK && !rt::h2d_async(d_in, in, ib, s)) rc = fail(B200FFT_ERR_CUDA, rt::last_error());
+    if (rc == B200FFT_OK) rc = real_exec_device(rp, inverse, d_in, d_out, batch, s);
+    if (rc == B200FFT_OK && !(rt::d2h_async(out, d_out, ob, s) && rt::stream_sync(s))) rc = fail(B200FFT_ERR_CUDA, rt::last_error());
+    if (s) {
+        rt::stream_sync(s);
+        rt::stream_destroy(s);
+    }
+    if (d_in) rt::dfree(d_in);
+    if (d_out) rt::dfree(d_out);
+    return rc;
+}
+}  // namespace b2
+
+extern "C" {
+
+int b200fft_real_plan_create(b200fft_real_plan** out, uint64_t len, int precision, int device) {
+    if (!out) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (len < 2 || (len & 1)) return b2::fail(B200FFT_ERR_UNSUPPORTED, "real transforms need an even length >= 2");
+    if (precision != B200FFT_F32 && precision != B200FFT_F64) return b2::fail(B200FFT_ERR_INVALID_ARG, "unknown precision");
+    std::unique_ptr<b200fft_real_plan> rp(new b200fft_real_plan());
+    rp->len = len;
+    rp->M = len / 2;
+    rp->precision = precision;
+    rp->device = device;
+    int rc = b200fft_plan_create(&rp->fwd, rp->M, B200FFT_FORWARD, precision, device);
+    if (rc == B200FFT_OK) rc = b200fft_plan_create(&rp->inv, rp->M, B200FFT_INVERSE, precision, device);
+    if (rc != B200FFT_OK) return rc;
+    const uint64_t h = rp->M / 2 + 1;
+    if (precision == B200FFT_F32) {
+        std::vector<b2::cx<float>> t((size_t)h);
+        for (uint64_t k = 0; k < h; ++k) t[(size_t)k] = b2::hm::twiddle<float>(k, len);
+        rp->tw = b2::rt::dmalloc(h * 8);
+        if (!rp->tw || !b2::rt::h2d_sync(rp->tw, t.data(), h * 8)) return b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    } else {
+        std::vector<b2::cx<double>> t((size_t)h);
+        for (uint64_t k = 0; k < h; ++k) t[(size_t)k] = b2::hm::twiddle<double>(k, len);
+        rp->tw = b2::rt::dmalloc(h * 16);
+        if (!rp->tw || !b2::rt::h2d_sync(rp->tw, t.data(), h * 16)) return b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    }
+    *out = rp.release();
+    return B200FFT_OK;
+}
+int b200fft_real_plan_destroy(b200fft_real_plan* plan) {
+    if (!plan) return B200FFT_OK;
+    b2::rt::set_device(plan->device);
+    delete plan;
+    return B200FFT_OK;
+}
+uint64_t b200fft_real_workspace_bytes(const b200fft_real_plan* plan, uint64_t batch) {
+    if (!plan) return 0;
+    const uint64_t esz = plan->precision == B200FFT_F32 ? 8 : 16;
+    return (batch * plan->M * esz + 255) / 256 * 256 + std::max(plan->fwd->work_bytes(batch), plan->inv->work_bytes(batch)) + 256;
+}
+int b200fft_real_forward_device(const b200fft_real_plan* plan, const void* d_real_in, void* d_complex_out, uint64_t batch, void* cuda_stream) {
+    return b2::real_exec_device(plan, false, d_real_in, d_complex_out, batch, (b2::rt::stream_t)cuda_stream);
+}
+int b200fft_real_inverse_device(const b200fft_real_plan* plan, const void* d_complex_in, void* d_real_out, uint64_t batch, void* cuda_stream) {
+    return b2::real_exec_device(plan, true, d_complex_in, d_real_out, batch, (b2::rt::stream_t)cuda_stream);
+}
+int b200fft_real_forward_host(const b200fft_real_plan* plan, const void* real_in, void* complex_out, uint64_t batch) {
+    return b2::real_exec_host(plan, false, real_in, complex_out, batch);
+}
+int b200fft_real_inverse_host(const b200fft_real_plan* plan, const void* complex_in, void* real_out, uint64_t batch) {
+    return b2::real_exec_host(plan, true, complex_in, real_out, batch);
 }
 
 const char* b200fft_last_error(void) { return b2::g_last_error.c_str(); }

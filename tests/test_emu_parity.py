@@ -92,6 +92,14 @@ def test_compiled_tile_lengths_in_both_roles(lib):
         assert f.describe() == "SmoothFourStep{%dx%d,compiled}" % (a, b)
 
 
+@pytest.mark.parametrize("rdtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_real_fft_wrappers(lib, rdtype):
+    """r2c / c2r of even lengths on top of the complex plans (tests/real_fft_cases.py)."""
+    import real_fft_cases
+
+    real_fft_cases.check_real_fft(rb.RealFftPlanner(rdtype, lib=lib), rdtype)
+
+
 def test_random_smooth_composites(planner):
     """Seeded random products of primes <= 31 between the one-pass limit and 600 000: every radix list / split the
     planner can produce for SmoothFourStep, against the f64 truth."""

@@ -263,6 +263,28 @@ def test_sharded_scatter_fft_gather_two_gpus(torch_cuda):
     assert r.returncode == 0 and "SHARDED-OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("rdtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_real_fft_wrappers(torch_cuda, rdtype):
+    """r2c / c2r of even lengths on top of the complex plans: host entry points (tests/real_fft_cases.py) and the device ones."""
+    import real_fft_cases
+
+    torch = torch_cuda
+    pl = rb.RealFftPlanner(rdtype)
+    real_fft_cases.check_real_fft(pl, rdtype)
+    n, batch = 4096, 300
+    f = pl.plan_fft(n)
+    x = (np.random.default_rng(1).random(n * batch) * 10).astype(rdtype)
+    X = np.zeros(batch * (n // 2 + 1), np.complex64 if rdtype == np.float32 else np.complex128)
+    f.forward(x, X)
+    dx = torch.from_numpy(x).cuda()
+    dX = torch.empty(batch * (n // 2 + 1), dtype=torch.complex64 if rdtype == np.float32 else torch.complex128, device="cuda")
+    f.forward(dx, dX)
+    assert np.array_equal(dX.cpu().numpy(), X)
+    back = torch.empty_like(dx)
+    f.inverse(dX, back)
+    assert rel_l2(back.cpu().numpy() / n, x) <= 2 * strict_bound(n, X.dtype)
+
+
 def test_host_pipeline_many_chunks(torch_cuda):
     """Host-slice path with more 64 MiB staging chunks than ring slots (4): 6.x chunks, pageable and pinned."""
     torch = torch_cuda

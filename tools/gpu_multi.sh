@@ -8,11 +8,11 @@ export PYTHONPATH=$PWD:$PWD/tests
 nvidia-smi --query-gpu=index,name,pci.bus_id --format=csv > $OUT/env.txt 2>&1
 nvidia-smi topo -m >> $OUT/env.txt 2>&1
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "sharded" > $OUT/pytest_sharded.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_sharded.log; tail -3 $OUT/pytest_sharded.log
-NCCL_DEBUG=WARN timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 tail -5 $OUT/bench.err
 python - $OUT <<'PY'
 import json, sys
-d=json.load(open(sys.argv[1] + '/bench.json'))
+d=json.loads([l for l in open(sys.argv[1] + '/bench.json') if l.startswith('{')][-1])
 print("n_gpus", d["n_gpus"], "value", d["value"], "frac", d["roofline"]["frac"], "ms", d["ms_per_step"])
 print("e2e", json.dumps(d["e2e"])[:600])
 for r in d.get("other_configs") or []:
