@@ -3,6 +3,7 @@
 OUT=gpurun_out/s7
 mkdir -p $OUT
 export PYTHONPATH=$PWD:$PWD/tests
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -7 $OUT/smoke.log
 timeout 300 python tools/ab_two_pass.py 15,16,17,18,19,20 > $OUT/ab_two_pass_default.txt 2>&1; tail -1 $OUT/ab_two_pass_default.txt
 B200FFT_FUSED_NOCOMPUTE=1 timeout 300 python tools/ab_two_pass.py 15,16,17,18,19,20 > $OUT/ab_two_pass_nocompute.txt 2>&1; tail -1 $OUT/ab_two_pass_nocompute.txt
