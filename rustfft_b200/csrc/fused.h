@@ -312,6 +312,7 @@ run_fused(const __grid_constant__ typename FusedKernel<KA, KB, NG, NS>::Params p
         const int ltid = tid - g * NTG;
         const int bar_id = 1 + g;
         constexpr bool DA = KA::DIRECT_OUT;  // pass-A results go from the registers to the tile-major ring
+        constexpr bool DB = KB::DIRECT_OUT;  // pass-B results go from the registers to the caller's output
         FusedTrace tr;
         tr.init(ltid == 0 ? p.trace : nullptr, 2 + (g & 1));
         for (uint32_t i = (uint32_t)g;; i += NG) {
@@ -349,8 +350,15 @@ run_fused(const __grid_constant__ typename FusedKernel<KA, KB, NG, NS>::Params p
                 KB::prefetch(p.b, bid, ltid, r);
                 tma::mbar_wait(&full[s], ph);
                 tr.stamp(0x80u | s);
-                if (!(p.flags & 1u)) GroupPhases<KB, 0>::run(p.b, bid, ltid, r, buf, bar_id, nullptr);
-                else tma::fence_proxy_async();
+                if (!(p.flags & 1u)) {
+                    GroupPhases<KB, 0>::run(p.b, bid, ltid, r, buf, bar_id, DB ? &empty[s] : nullptr);
+                    if constexpr (DB) via_smem = false;  // the stage was handed back after the last exchange read
+                } else if (DB) {
+                    if (ltid == 0) tma::mbar_arrive(&empty[s]);
+                    via_smem = false;
+                } else {
+                    tma::fence_proxy_async();
+                }
             }
             if (via_smem) {
                 // every thread has written its share of the dense output tile and fenced it towards the async proxy

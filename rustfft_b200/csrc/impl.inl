@@ -421,6 +421,15 @@ static bool fused_tw2() {
     }();
     return v;
 }
+// B200FFT_FUSED_BDIRECT = bit mask over log2 N - 15: pass B of the fused kernel stores its results from the registers (coalesced 64-256
+// byte runs) instead of through a TMA store of the stage; measured per size (profiles/), default = the sizes where it won
+static bool fused_bdirect(uint32_t lgN) {
+    static uint32_t v = [] {
+        const char* e = std::getenv("B200FFT_FUSED_BDIRECT");
+        return e ? (uint32_t)std::atoi(e) : 0u;
+    }();
+    return lgN >= 15 && lgN < 47 && ((v >> (lgN - 15)) & 1u);
+}
 static bool fused_trace() {
     static bool v = [] {
         const char* e = std::getenv("B200FFT_FUSED_TRACE");
@@ -887,7 +896,7 @@ struct Builder {
         return false;
     }
     // ---- fused single-launch variant (fused.h: run_fused) ----
-    template <int L1, int L2, bool SW, bool TILED = true>
+    template <int L1, int L2, bool SW, bool TILED = true, bool DOUT = false>
     static bool make_fused_t(b200fft_plan& pl, uint32_t lgN, const C* full_tw, FusedFn& fn, uint32_t& W_out) {
         if constexpr (sizeof(T) == 4) {
             using GA = typename FusedGeo<T, L1>::type;
@@ -895,9 +904,12 @@ struct Builder {
             if constexpr (TILED) {
                 if (!fused_tiled()) return make_fused_t<L1, L2, SW, false>(pl, lgN, full_tw, fn, W_out);
             }
+            if constexpr (!TILED && !DOUT) {
+                if (fused_bdirect(lgN)) return make_fused_t<L1, L2, SW, false, true>(pl, lgN, full_tw, fn, W_out);
+            }
             // TILED: tile-major ring -- pass A stores straight from its registers, pass B gathers its rows with one 4-D tensor copy
             using KA = TmaTileKernel<GA, FF, FF, 0, SW, TILED ? 1 : 0>;
-            using KB = TmaTileKernel<GB, JF, FF, 1, SW, TILED ? GA::F : 0>;
+            using KB = TmaTileKernel<GB, JF, FF, 1, SW, TILED ? GA::F : 0, DOUT>;
             using FK = FusedKernel<KA, KB, FUSED_NG, FUSED_NS>;
             static_assert(FK::SMEM_BYTES <= MAX_SMEM_PER_CTA, "fused stages must fit one SM");
             const uint32_t lg1 = hm::ilog2(L1), lg2 = hm::ilog2(L2);
@@ -1268,7 +1280,8 @@ struct Builder {
             }
             return ok;
         };
-        pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) + (fused ? ",fused,ring=" + std::to_string(fused_w) : std::string()) + "}";
+        pl.desc = "FourStep{" + std::to_string(N1) + "x" + std::to_string(N2) +
+                  (fused ? ",fused,ring=" + std::to_string(fused_w) + (fused_bdirect(lgN) && !fused_tiled() ? ",bdirect" : "") : std::string()) + "}";
         set_recipe(pl, B200FFT_RECIPE_POW2);
         pl.chunk = fused ? fused_w : chunk;
         return true;

@@ -1205,7 +1205,10 @@ template <class G> struct RL_last_pow2 {
 //       never touch the TMA store path (49 GB/s per SM, measured: the scarce resource of the fused kernel);
 //   ROLE 1, TILED = F of pass A: the tile (F rows x L columns) is gathered by one 4-D tensor copy [all TA tiles][F rows]
 //       [FO columns] and lands as [tile][row][column-in-tile]; phase 0 reads it with that index map.
-template <class G, Map M0, Map M1, int ROLE, bool SW, int TILED = 0>
+//   ROLE 1, DOUT: the finished rows go from the registers straight to the caller's output (runs of F consecutive k1, 64-256 bytes)
+//       instead of through the dense tile and a TMA store: the shared-memory stage is free after the last exchange read and the SM's
+//       TMA unit only carries the three other transfers of a tile pair (fused.h, B200FFT_FUSED_BDIRECT)
+template <class G, Map M0, Map M1, int ROLE, bool SW, int TILED = 0, bool DOUT = false>
 struct TmaTileKernel {
     using T = typename G::T;
     using Eng = Engine<G, M0, M1>;
@@ -1241,7 +1244,7 @@ struct TmaTileKernel {
         uint32_t ring_w;         // fused single-launch plans (fused.h): the workspace is a ring of ring_w transform slots --
                                  //   ROLE 0 stores to / ROLE 1 loads from slot (transform mod ring_w); 0 = plain chunk workspace
     };
-    static constexpr bool DIRECT_OUT = (ROLE == 0 && TILED != 0);  // registers -> tile-major ring
+    static constexpr bool DIRECT_OUT = (ROLE == 0 && TILED != 0) || (ROLE == 1 && DOUT);  // registers -> tile-major ring | output
     static constexpr int FO = (ROLE == 1 && TILED > 0) ? TILED : 1;  // ROLE 1: columns per pass-A tile
     static constexpr int TA = G::L / FO;                             // ROLE 1: pass-A tiles per transform
     static constexpr int TBOX = TA < 256 ? TA : 256;                 // tiles per tensor copy
@@ -1427,7 +1430,13 @@ struct TmaTileKernel {
             if constexpr (P == NPHASE - 2) {
                 int f, j;
                 Eng::out_owner(tid, f, j);
-                if constexpr (DIRECT_OUT) {
+                if constexpr (ROLE == 1 && DOUT) {
+                    // row k1 = c0 + f, output k2 = j + TP q -> out[b N + k2 N1 + k1]: consecutive threads = consecutive k1
+                    const Where w = where(p, bid);
+                    cx<T>* dst = p.out + ((uint64_t)zout(p, w.b) << p.lgN) + w.c0 + f + ((size_t)j << p.lg_other);
+                    B2_UNROLL
+                    for (int q = 0; q < G::E; ++q) st_cs(dst + ((size_t)(G::TP * q) << p.lg_other), SW ? swap_ri(r.v[q]) : r.v[q]);
+                } else if constexpr (DIRECT_OUT) {
                     // natural-order results -> the tile-major ring: the dense tile [row][f] is the memory layout, consecutive
                     // threads = consecutive f then consecutive rows, i.e. every warp instruction writes 256 contiguous bytes
                     const Where w = where(p, bid);

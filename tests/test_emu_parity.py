@@ -203,9 +203,9 @@ def test_fused_four_step_batches(lib):
                                  {"B200FFT_FLOW": "1", "B200FFT_FLOW_LOOKAHEAD": "3000"}, {"B200FFT_FUSED": "0", "B200FFT_NARROW": "1"},
                                  {"B200FFT_FUSED": "0", "B200FFT_NARROW": "1", "B200FFT_TMA_TILES": "0"},
                                  {"B200FFT_FUSED_W": "2"}, {"B200FFT_FUSED_LOOKAHEAD": "40"}, {"B200FFT_FUSED_LOOKAHEAD": "5000"},
-                                 {"B200FFT_FUSED_TILED": "1"}],
+                                 {"B200FFT_FUSED_TILED": "1"}, {"B200FFT_FUSED_BDIRECT": "63"}],
                          ids=["chunked-tma-tiles", "chunked-ldg-tiles", "flow", "flow-ring2", "flow-deep-lookahead", "narrow-tma-tiles",
-                              "narrow-ldg-tiles", "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead", "fused-tile-major-ring"])
+                              "narrow-ldg-tiles", "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead", "fused-tile-major-ring", "fused-direct-pass-b-output"])
 def test_two_pass_variants_in_a_fresh_process(env):
     """The library reads its switches once per process: the chunked launch pairs (B200FFT_FUSED=0; TMA tiles or LDG/STG passes), the
     fused kernel with other ring sizes, and the single-launch dataflow kernel (B200FFT_FLOW=1, several ring sizes) are replayed in processes of their own; the

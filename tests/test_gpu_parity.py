@@ -225,10 +225,11 @@ def test_device_path_equals_host_path_and_workspace_variants(torch_cuda):
     {"B200FFT_FUSED_LOOKAHEAD": "40"},              # ... with a short look-ahead
     {"B200FFT_FUSED_LOOKAHEAD": "5000"},            # ... and a deep one
     {"B200FFT_FUSED_TILED": "1"},                   # ... with the tile-major ring (pass A stores from its registers)
+    {"B200FFT_FUSED_BDIRECT": "63"},                # ... with pass B storing its results from the registers (no TMA store)
     {"B200FFT_FLOW": "1"},                          # two-pass plans as one launch of the (round-1) dataflow kernel
     {"B200FFT_FLOW": "1", "B200FFT_FLOW_W": "2"},   # ... with the smallest ring (every tile waits)
 ], ids=["tma-pipelined", "radix16", "chunked", "chunked-one-stream", "chunked-four-streams-small-chunks", "host-two-stream", "chunked-ldg-tiles",
-        "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead", "fused-tile-major-ring", "flow", "flow-ring2"])
+        "fused-ring2", "fused-short-lookahead", "fused-deep-lookahead", "fused-tile-major-ring", "fused-direct-pass-b-output", "flow", "flow-ring2"])
 def test_alternative_code_paths_in_a_fresh_process(torch_cuda, env):
     import os
     import subprocess
