@@ -448,10 +448,16 @@ static uint32_t fused_ring_slots(uint32_t per_round, uint64_t bytes_per_transfor
         return (uint32_t)(k < 1 ? 1 : k);
     }();
     if (forced >= 2) return forced;
-    uint32_t D = (look + per_round - 1) / per_round;
+    // measured ring sweep (profiles/r2j_ab_fused_ring_size.txt): 2^18 is best at 32 slots (64 MiB: 0.591 against 0.485 at 16 and 0.572 at
+    // 48), 2^19 at 16-20 slots (0.578 / 0.582), 2^20 at 10 slots = 80 MiB (0.561 against 0.541 at 8 and 0.530 at 12): from 8 MiB
+    // transforms on, one more pair of slots than the 1000-ticket look-ahead asks for, and the residency cap that allows it
+    const bool big = bytes_per_transform >= (8ull << 20);
+    const uint32_t lk = big ? std::max<uint32_t>(look, 1280u) : look;
+    const uint64_t cap = big ? (80ull << 20) : (64ull << 20);
+    uint32_t D = (lk + per_round - 1) / per_round;
     if (D < 1) D = 1;
     uint32_t W = 2 * D;
-    while (W > 2 && (uint64_t)W * bytes_per_transform > (64ull << 20)) W -= 2;  // the ring must stay L2 resident
+    while (W > 2 && (uint64_t)W * bytes_per_transform > cap) W -= 2;  // the ring must stay L2 resident
     return W;
 }
 
