@@ -28,7 +28,15 @@ def main():
         if metric != "gpu__time_duration.sum":
             continue
         name = r[col["Kernel Name"]]
-        if "TmaTileKernel" in name or "run_flow" in name:
+        if "run_fused" in name:
+            # fused single-launch four-step: the two tile kernels it runs (pass A L1-point columns, pass B L2-point rows)
+            g = re.findall(r"Geo<(\w+), (\d+), (\d+), (\d+)", name)
+            key = (f"b2::run_fused fused four-step (both passes, one persistent launch) {g[0][0]} {g[0][1]}x{g[1][1] if len(g) > 1 else g[0][1]} "
+                   f"grid={r[col['Grid Size']]} block={r[col['Block Size']]}")
+        elif "run_cluster" in name:
+            g = re.findall(r"Geo<(\w+), (\d+), (\d+), (\d+)", name)
+            key = f"b2::run_cluster cluster plan {g[0][0]} L={g[0][1]} grid={r[col['Grid Size']]} block={r[col['Block Size']]}"
+        elif "TmaTileKernel" in name or "run_flow" in name:
             m = re.search(r"Geo<(\w+), (\d+), (\d+), (\d+)", name)
             role = re.search(r">, \d, \d, (\d), \d>", name)
             kind = "dataflow four-step (both passes)" if "run_flow" in name else (
