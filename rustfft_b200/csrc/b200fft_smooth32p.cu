@@ -1,0 +1,4 @@
+// libb200fft.so: f32 run-time-radix two-pass kernels with the prime butterflies
+#include "rt_cuda.h"
+#define B2_PART_SMOOTH32P 1
+#include "impl.inl"

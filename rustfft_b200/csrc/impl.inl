@@ -41,8 +41,11 @@ inline int fail(int code, const std::string& msg) {
 // which parts this translation unit compiles (b200fft.cu / b200fft_f32.cu / b200fft_f64.cu; the CPU replay
 // harness defines none and gets everything)
 #if !defined(B2_PART_CABI) && !defined(B2_PART_F32) && !defined(B2_PART_F64) && !defined(B2_PART_SMOOTH32) && !defined(B2_PART_SMOOTH64) && \
-    !defined(B2_PART_FUSED32) && !defined(B2_PART_CTILE32) && !defined(B2_PART_SMOOTH32S) && !defined(B2_PART_SMOOTH64S)
+    !defined(B2_PART_FUSED32) && !defined(B2_PART_CTILE32) && !defined(B2_PART_SMOOTH32S) && !defined(B2_PART_SMOOTH64S) && \
+    !defined(B2_PART_SMOOTH32P) && !defined(B2_PART_SMOOTH64P)
 #define B2_PART_FUSED32 1
+#define B2_PART_SMOOTH32P 1
+#define B2_PART_SMOOTH64P 1
 #define B2_PART_CTILE32 1
 #define B2_PART_SMOOTH32S 1
 #define B2_PART_SMOOTH64S 1
@@ -531,6 +534,8 @@ bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_small_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 bool build_smooth_small_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+bool build_smooth_passes_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
+bool build_smooth_passes_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b);
 // single-pass cluster plans (cluster.h), compiled in the same translation unit as the fused kernels
 bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half);
 // compiled composite tiles (b200fft_ctile32.cu)
@@ -556,25 +561,35 @@ struct Builder {
     }
     static bool smooth_dispatch(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
         const bool small = smooth_kind_is_small(pl, kind, a, b);
-        if constexpr (sizeof(T) == 4)
-            return small ? build_smooth_small_f32(pl, kind, a, b) : build_smooth_f32(pl, kind, a, b);
-        else
-            return small ? build_smooth_small_f64(pl, kind, a, b) : build_smooth_f64(pl, kind, a, b);
+        const bool two_pass = kind == 1 || kind == 4 || kind == 5 || kind == 6;
+        if constexpr (sizeof(T) == 4) {
+            if (small) return build_smooth_small_f32(pl, kind, a, b);
+            return two_pass ? build_smooth_passes_f32(pl, kind, a, b) : build_smooth_f32(pl, kind, a, b);
+        } else {
+            if (small) return build_smooth_small_f64(pl, kind, a, b);
+            return two_pass ? build_smooth_passes_f64(pl, kind, a, b) : build_smooth_f64(pl, kind, a, b);
+        }
     }
     // kind 0: Smooth; 1: SmoothFourStep{a x b}; 2: one-pass Rader, outer radix a, prime b; 3: one-pass Bluestein, inner M = a;
     //      4: GoodThomas{a x b}; 5: Rader over SmoothFourStep{a x b}; 6: Bluestein over SmoothFourStep{a x b}
+    // (one-pass kinds 0 / 2 / 3 and two-pass kinds 1 / 4 / 5 / 6 are instantiated in different translation units: build time)
     template <int RMAX>
-    static bool smooth_build_here(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+    static bool smooth_build_onepass(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+        const bool sw = pl.direction != 0;
+        if (kind == 2) return sw ? make_smooth_conv_t<true, RMAX>(pl, 0, a, b) : make_smooth_conv_t<false, RMAX>(pl, 0, a, b);
+        if (kind == 3) return sw ? make_smooth_conv_t<true, RMAX>(pl, 1, 1, a) : make_smooth_conv_t<false, RMAX>(pl, 1, 1, a);
+        std::vector<uint32_t> radices;
+        if (kind != 0 || !smooth_factor(pl.len, radices)) return false;
+        return sw ? make_smooth_t<true, RMAX>(pl, radices) : make_smooth_t<false, RMAX>(pl, radices);
+    }
+    template <int RMAX>
+    static bool smooth_build_twopass(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
         const bool sw = pl.direction != 0;
         if (kind == 1 || kind == 4)
             return sw ? make_smooth_four_step_t<true, RMAX>(pl, a, b, kind == 4 ? 1 : 0) : make_smooth_four_step_t<false, RMAX>(pl, a, b, kind == 4 ? 1 : 0);
-        if (kind == 2) return sw ? make_smooth_conv_t<true, RMAX>(pl, 0, a, b) : make_smooth_conv_t<false, RMAX>(pl, 0, a, b);
-        if (kind == 3) return sw ? make_smooth_conv_t<true, RMAX>(pl, 1, 1, a) : make_smooth_conv_t<false, RMAX>(pl, 1, 1, a);
         if (kind == 5 || kind == 6)
             return sw ? make_smooth_big_conv_t<true, RMAX>(pl, a, b, kind == 5) : make_smooth_big_conv_t<false, RMAX>(pl, a, b, kind == 5);
-        std::vector<uint32_t> radices;
-        if (!smooth_factor(pl.len, radices)) return false;
-        return sw ? make_smooth_t<true, RMAX>(pl, radices) : make_smooth_t<false, RMAX>(pl, radices);
+        return false;
     }
 
     // ---------------- Direct ----------------
@@ -2424,10 +2439,15 @@ int build_plan_f32(b200fft_plan& pl) { return Builder<float>::build(pl); }
 int build_plan_f64(b200fft_plan& pl) { return Builder<double>::build(pl); }
 #endif
 #if defined(B2_PART_SMOOTH32)
-bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here<31>(pl, kind, a, b); }
+bool build_smooth_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_onepass<31>(pl, kind, a, b); }
+#endif
+#if defined(B2_PART_SMOOTH32P)
+bool build_smooth_passes_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_twopass<31>(pl, kind, a, b); }
 #endif
 #if defined(B2_PART_SMOOTH32S)
-bool build_smooth_small_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<float>::smooth_build_here<16>(pl, kind, a, b); }
+bool build_smooth_small_f32(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+    return (kind == 0 || kind == 2 || kind == 3) ? Builder<float>::smooth_build_onepass<16>(pl, kind, a, b) : Builder<float>::smooth_build_twopass<16>(pl, kind, a, b);
+}
 #endif
 #if defined(B2_PART_FUSED32)
 bool build_cluster_f32(b200fft_plan& pl, uint32_t lgN, bool half) { return Builder<float>::cluster_build_here(pl, lgN, half); }
@@ -2440,10 +2460,15 @@ bool build_fused_f32(b200fft_plan& pl, uint32_t L1, uint32_t L2, uint32_t lgN, c
 bool build_compiled_smooth_f32(b200fft_plan& pl, uint32_t a, uint32_t b) { return Builder<float>::compiled_smooth_build_here(pl, a, b); }
 #endif
 #if defined(B2_PART_SMOOTH64)
-bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here<31>(pl, kind, a, b); }
+bool build_smooth_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_onepass<31>(pl, kind, a, b); }
+#endif
+#if defined(B2_PART_SMOOTH64P)
+bool build_smooth_passes_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_twopass<31>(pl, kind, a, b); }
 #endif
 #if defined(B2_PART_SMOOTH64S)
-bool build_smooth_small_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) { return Builder<double>::smooth_build_here<16>(pl, kind, a, b); }
+bool build_smooth_small_f64(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
+    return (kind == 0 || kind == 2 || kind == 3) ? Builder<double>::smooth_build_onepass<16>(pl, kind, a, b) : Builder<double>::smooth_build_twopass<16>(pl, kind, a, b);
+}
 #endif
 
 }  // namespace b2

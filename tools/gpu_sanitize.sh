@@ -15,7 +15,9 @@ run() {  # name tool env...
 run default_memcheck memcheck
 run default_racecheck racecheck
 run default_synccheck synccheck
+if [ -z "$SANITIZE_DEFAULT_ONLY" ]; then
 run chunked_racecheck racecheck B200FFT_FUSED=0 SANITIZE_QUICK=1
 run flow_memcheck memcheck B200FFT_FLOW=1 SANITIZE_QUICK=1
 run pipelined_racecheck racecheck B200FFT_PIPELINE=1 SANITIZE_QUICK=1
+fi
 for f in $OUT/*.log; do echo "--- $f"; grep -E "^ok|SUMMARY|rc=|Error|error|Race|Hazard" $f | head -60; done > $OUT/summary.txt
