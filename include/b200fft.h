@@ -95,7 +95,8 @@ enum {
     B200FFT_RECIPE_GOOD_THOMAS = 4,
     B200FFT_RECIPE_RADER = 5,
     B200FFT_RECIPE_BLUESTEIN = 6,
-    B200FFT_RECIPE_CLUSTER = 7
+    B200FFT_RECIPE_CLUSTER = 7,
+    B200FFT_RECIPE_COLUMNS = 8 /* internal to the 2-D plans: len = a * b, a-point FFTs down the columns of [a][b] images */
 };
 typedef struct b200fft_recipe_node {
     uint32_t kind;  /* B200FFT_RECIPE_* */
@@ -151,6 +152,15 @@ int b200fft_real_forward_device(const b200fft_real_plan* plan, const void* d_rea
 int b200fft_real_inverse_device(const b200fft_real_plan* plan, const void* d_complex_in, void* d_real_out, uint64_t batch, void* cuda_stream);
 int b200fft_real_forward_host(const b200fft_real_plan* plan, const void* real_in, void* complex_out, uint64_t batch);
 int b200fft_real_inverse_host(const b200fft_real_plan* plan, const void* complex_in, void* real_out, uint64_t batch);
+
+/* 2-D complex transforms of row-major [height][width] images (batch of them, contiguous): the width-point plan over all rows, then one
+ * strided pass of height-point FFTs down the columns (the same two steps a caller of RustFFT writes with two plans and two
+ * transposes).  height: prime factors <= 31 and at most 4096 (f64: 2048); width: any length b200fft_plan_create accepts. */
+typedef struct b200fft_plan2d b200fft_plan2d;
+int b200fft_plan2d_create(b200fft_plan2d** out, uint64_t height, uint64_t width, int direction, int precision, int device);
+int b200fft_plan2d_destroy(b200fft_plan2d* plan);
+int b200fft_exec2d_device(const b200fft_plan2d* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream);
+int b200fft_exec2d_host(const b200fft_plan2d* plan, const void* in, void* out, uint64_t batch);
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* b200fft_last_error(void);

@@ -26,7 +26,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "Recipe", "RealFftPlanner", "RealFft", "default_library", "shard_range"]
+__all__ = ["FftDirection", "FftPlanner", "Fft", "Library", "FftError", "Recipe", "RealFftPlanner", "RealFft", "Fft2d", "default_library", "shard_range"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200FFT_LIB: load another build of the same C ABI (A/B measurements of kernel variants; tools/ab_two_pass.py)
@@ -126,6 +126,7 @@ class Library:
         "b200fft_workspace_bytes", "b200fft_exec_device_ws", "b200fft_last_error", "b200fft_version",
         "b200fft_real_plan_create", "b200fft_real_plan_destroy", "b200fft_real_workspace_bytes", "b200fft_real_forward_device",
         "b200fft_real_inverse_device", "b200fft_real_forward_host", "b200fft_real_inverse_host",
+        "b200fft_plan2d_create", "b200fft_plan2d_destroy", "b200fft_exec2d_device", "b200fft_exec2d_host",
     ]
 
     def __init__(self, path: str = DEFAULT_LIB_PATH):
@@ -165,6 +166,10 @@ class Library:
         c.b200fft_real_inverse_device.argtypes = [vp, vp, vp, u64, vp]
         c.b200fft_real_forward_host.argtypes = [vp, vp, vp, u64]
         c.b200fft_real_inverse_host.argtypes = [vp, vp, vp, u64]
+        c.b200fft_plan2d_create.argtypes = [ctypes.POINTER(vp), u64, u64, i32, i32, i32]
+        c.b200fft_plan2d_destroy.argtypes = [vp]
+        c.b200fft_exec2d_device.argtypes = [vp, vp, vp, u64, vp]
+        c.b200fft_exec2d_host.argtypes = [vp, vp, vp, u64]
 
     def device_count(self) -> int:
         n = ctypes.c_int(0)
@@ -388,11 +393,61 @@ class FftPlanner:
         """Planning owned by the caller: build exactly the decomposition `recipe` names (not cached)."""
         return Fft(self._lib, recipe.len, FftDirection(direction), self._precision, self.device, recipe=recipe)
 
+    def plan_fft_2d(self, height: int, width: int, direction: FftDirection = FftDirection.Forward) -> Fft2d:
+        """2-D transform of [height][width] images: the width-point plan over the rows, one strided pass down the columns."""
+        return Fft2d(self._lib, height, width, direction, self._precision, self.device)
+
     def plan_fft_forward(self, len: int) -> Fft:
         return self.plan_fft(len, FftDirection.Forward)
 
     def plan_fft_inverse(self, len: int) -> Fft:
         return self.plan_fft(len, FftDirection.Inverse)
+
+
+class Fft2d:
+    """2-D complex transform of row-major [height][width] images (a batch of them, contiguous): unnormalised, forward sign as in 1-D.
+    numpy arrays go through the synchronous host entry point (in place), torch CUDA tensors through the device one (in place or into
+    `out`, asynchronous on torch's current stream)."""
+
+    def __init__(self, lib: Library, height: int, width: int, direction: FftDirection, precision: int, device: int):
+        self._lib, self.height, self.width, self._precision, self.device = lib, int(height), int(width), precision, device
+        self._direction = FftDirection(direction)
+        self._h = ctypes.c_void_p()
+        lib.check(lib.c.b200fft_plan2d_create(ctypes.byref(self._h), self.height, self.width, int(direction), precision, device))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.c.b200fft_plan2d_destroy(h)
+            except Exception:
+                pass
+
+    def fft_direction(self) -> FftDirection:
+        return self._direction
+
+    def process(self, buffer: np.ndarray) -> None:
+        want = np.complex64 if self._precision == F32 else np.complex128
+        if buffer.dtype != want or not buffer.flags.c_contiguous or not buffer.flags.writeable:
+            raise TypeError(f"Fft2d.process wants a contiguous writable {np.dtype(want)} array")
+        per = self.height * self.width
+        if buffer.size % per:
+            raise FftError(-5, f"Input FFT buffer must be a multiple of FFT length. Expected multiple of {per}, got len = {buffer.size}")
+        self._lib.check(self._lib.c.b200fft_exec2d_host(self._h, buffer.ctypes.data, buffer.ctypes.data, buffer.size // per))
+
+    def process_device(self, x, out=None):
+        import torch
+
+        want = torch.complex64 if self._precision == F32 else torch.complex128
+        dst = x if out is None else out
+        if x.dtype != want or dst.dtype != want or not x.is_cuda or not x.is_contiguous() or not dst.is_contiguous() or dst.numel() != x.numel():
+            raise TypeError(f"Fft2d.process_device wants contiguous CUDA tensors of {want} with equal sizes")
+        per = self.height * self.width
+        if x.numel() % per:
+            raise FftError(-5, f"Input FFT buffer must be a multiple of FFT length. Expected multiple of {per}, got len = {x.numel()}")
+        self._lib.check(self._lib.c.b200fft_exec2d_device(self._h, x.data_ptr(), dst.data_ptr(), x.numel() // per,
+                                                          torch.cuda.current_stream(x.device).cuda_stream))
+        return dst
 
 
 class RealFft:

@@ -556,12 +556,13 @@ struct Builder {
             case 0: return smooth_factor(pl.len, r) && max_radix(r) <= 16;
             case 2: return smooth_factor((uint64_t)b - 1, r) && max_radix(r) <= 16;
             case 3: return smooth_factor(a, r) && max_radix(r) <= 16;
+            case 7: return smooth_factor(a, r) && max_radix(r) <= 16;
             default: return small_radices_only(a, b);
         }
     }
     static bool smooth_dispatch(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
         const bool small = smooth_kind_is_small(pl, kind, a, b);
-        const bool two_pass = kind == 1 || kind == 4 || kind == 5 || kind == 6;
+        const bool two_pass = kind == 1 || kind == 4 || kind == 5 || kind == 6 || kind == 7;
         if constexpr (sizeof(T) == 4) {
             if (small) return build_smooth_small_f32(pl, kind, a, b);
             return two_pass ? build_smooth_passes_f32(pl, kind, a, b) : build_smooth_f32(pl, kind, a, b);
@@ -582,9 +583,46 @@ struct Builder {
         if (kind != 0 || !smooth_factor(pl.len, radices)) return false;
         return sw ? make_smooth_t<true, RMAX>(pl, radices) : make_smooth_t<false, RMAX>(pl, radices);
     }
+    // stand-alone column pass of the 2-D plans: H-point FFTs down the columns of row-major [H][W] images, in place or out of place
+    template <bool SW, int RMAX>
+    static bool make_smooth_columns_t(b200fft_plan& pl, uint32_t H, uint32_t W) {
+        using KA = SmoothPassKernel<T, SW, 1, RMAX>;
+        std::vector<uint32_t> ra;
+        if (H > SMOOTH_MAX || !smooth_factor(H, ra)) return false;
+        typename KA::Params pa;
+        if (!fill_smooth_pass<KA>(pl, pa, H, ra)) return false;
+        const uint64_t N = (uint64_t)H * W;
+        pa.NN = N;
+        pa.other = W;
+        pa.div_other = make_fastdiv(W);
+        const uint32_t FA = std::max<uint32_t>(1, std::min<uint32_t>(64, SMOOTH_MAX / H));
+        pa.f_per_cta = FA;
+        pa.pitch = H;
+        pa.div_f = make_fastdiv(FA);
+        pa.smem_bytes = ra.size() > 1 ? (uint32_t)(2ull * FA * H * sizeof(C)) : 0;
+        pa.swap_out = SW ? 1u : 0u;
+        const size_t max_smem = 2ull * (SMOOTH_MAX + 64) * sizeof(C);
+        const uint64_t seg = std::max<uint64_t>(1, ((1ull << 31) - 1) / W);  // FFT indices of a launch stay below 2^31
+        pl.exec = [=](const ExecCtx& c) {
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += seg) {
+                const uint64_t nb = std::min(seg, c.batch - b0);
+                typename KA::Params q = pa;
+                q.in = (const C*)c.in + b0 * N;
+                q.out = (C*)c.out + b0 * N;
+                q.n_fft = nb * W;
+                if (!rt::launch_dyn<KA>(q, (q.n_fft + FA - 1) / FA, q.smem_bytes, max_smem, c.stream)) return false;
+            }
+            return true;
+        };
+        pl.launches = [=](uint64_t batch) { return (batch + seg - 1) / seg; };
+        pl.desc = "Columns{" + std::to_string(H) + " down [" + std::to_string(H) + "x" + std::to_string(W) + "]}";
+        set_recipe(pl, B200FFT_RECIPE_COLUMNS, H, W);
+        return true;
+    }
     template <int RMAX>
     static bool smooth_build_twopass(b200fft_plan& pl, int kind, uint32_t a, uint32_t b) {
         const bool sw = pl.direction != 0;
+        if (kind == 7) return sw ? make_smooth_columns_t<true, RMAX>(pl, a, b) : make_smooth_columns_t<false, RMAX>(pl, a, b);
         if (kind == 1 || kind == 4)
             return sw ? make_smooth_four_step_t<true, RMAX>(pl, a, b, kind == 4 ? 1 : 0) : make_smooth_four_step_t<false, RMAX>(pl, a, b, kind == 4 ? 1 : 0);
         if (kind == 5 || kind == 6)
@@ -2333,6 +2371,12 @@ struct Builder {
                 }
                 break;
             }
+            case B200FFT_RECIPE_COLUMNS: {
+                if (r.a < 2 || r.b < 1 || r.a * r.b != n || r.a > SMOOTH_MAX || !smooth_factor_any(r.a) || r.b >= (1ull << 31))
+                    return unsupported("COLUMNS: len = a * b, a smooth and at most the one-pass limit");
+                ok = smooth_dispatch(pl, 7, (uint32_t)r.a, (uint32_t)r.b);
+                break;
+            }
             case B200FFT_RECIPE_CLUSTER: {
                 if (sizeof(T) != 4 || !hm::is_pow2(n) || n < (1u << 14) || n > (1u << 17)) return unsupported("CLUSTER plans exist for f32, 2^14 .. 2^17");
                 if (r.a == 1 && n > (1u << 16)) return unsupported("half-tile CLUSTER plans exist for 2^14 .. 2^16");
@@ -2864,7 +2908,7 @@ int b200fft_plan_create_from_recipe(b200fft_plan** out, const b200fft_recipe_nod
     pl->precision = precision;
     pl->device = device;
     pl->recipe.assign(nodes, nodes + n_nodes);
-    if (!b2::hm::is_pow2(pl->len) && pl->len > (1ull << 23))
+    if (!b2::hm::is_pow2(pl->len) && pl->len > (1ull << 23) && nodes[0].kind != B200FFT_RECIPE_COLUMNS)
         return b2::fail(B200FFT_ERR_UNSUPPORTED, "non-power-of-two lengths above 2^23 are not planned by this build");
     const int rc = precision == B200FFT_F32 ? b2::build_plan_f32(*pl) : b2::build_plan_f64(*pl);
     if (rc != B200FFT_OK) return rc;
@@ -3060,6 +3104,71 @@ int b200fft_real_forward_host(const b200fft_real_plan* plan, const void* real_in
 }
 int b200fft_real_inverse_host(const b200fft_real_plan* plan, const void* complex_in, void* real_out, uint64_t batch) {
     return b2::real_exec_host(plan, true, complex_in, real_out, batch);
+}
+
+}  // extern "C"
+
+// ---- 2-D plans: rows through the width-point plan, then one strided column pass ---------------------------------------------
+struct b200fft_plan2d {
+    uint64_t H = 0, W = 0;
+    int precision = 0, device = 0;
+    b200fft_plan* rows = nullptr;
+    b200fft_plan* cols = nullptr;
+    ~b200fft_plan2d() {
+        if (rows) b200fft_plan_destroy(rows);
+        if (cols) b200fft_plan_destroy(cols);
+    }
+};
+
+extern "C" {
+
+int b200fft_plan2d_create(b200fft_plan2d** out, uint64_t height, uint64_t width, int direction, int precision, int device) {
+    if (!out) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (height < 1 || width < 1) return b2::fail(B200FFT_ERR_INVALID_ARG, "2-D plans need height >= 1 and width >= 1");
+    std::unique_ptr<b200fft_plan2d> p2(new b200fft_plan2d());
+    p2->H = height;
+    p2->W = width;
+    p2->precision = precision;
+    p2->device = device;
+    int rc = b200fft_plan_create(&p2->rows, width, direction, precision, device);
+    if (rc != B200FFT_OK) return rc;
+    if (height > 1) {
+        const b200fft_recipe_node node{B200FFT_RECIPE_COLUMNS, 0u, height * width, height, width};
+        rc = b200fft_plan_create_from_recipe(&p2->cols, &node, 1, direction, precision, device);
+        if (rc != B200FFT_OK) return rc;
+    }
+    *out = p2.release();
+    return B200FFT_OK;
+}
+int b200fft_plan2d_destroy(b200fft_plan2d* plan) {
+    delete plan;
+    return B200FFT_OK;
+}
+int b200fft_exec2d_device(const b200fft_plan2d* plan, const void* d_in, void* d_out, uint64_t batch, void* cuda_stream) {
+    if (!plan) return b2::fail(B200FFT_ERR_INVALID_ARG, "null plan");
+    int rc = b200fft_exec_device(plan->rows, d_in, d_out, batch * plan->H, cuda_stream);
+    if (rc == B200FFT_OK && plan->cols) rc = b200fft_exec_device(plan->cols, d_out, d_out, batch, cuda_stream);
+    return rc;
+}
+int b200fft_exec2d_host(const b200fft_plan2d* plan, const void* in, void* out, uint64_t batch) {
+    if (!plan || !in || !out) return b2::fail(B200FFT_ERR_INVALID_ARG, "null pointer");
+    if (batch == 0) return B200FFT_OK;
+    b2::rt::DeviceGuard guard(plan->device);
+    if (!guard.ok) return b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    const uint64_t bytes = batch * plan->H * plan->W * (plan->precision == B200FFT_F32 ? 8 : 16);
+    void* d = b2::rt::dmalloc(bytes);
+    b2::rt::stream_t s = b2::rt::stream_create();
+    int rc = (d && s) ? B200FFT_OK : b2::fail(B200FFT_ERR_CUDA, "staging allocation failed: " + b2::rt::last_error());
+    if (rc == B200FFT_OK && !b2::rt::h2d_async(d, in, bytes, s)) rc = b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    if (rc == B200FFT_OK) rc = b200fft_exec2d_device(plan, d, d, batch, s);
+    if (rc == B200FFT_OK && !(b2::rt::d2h_async(out, d, bytes, s) && b2::rt::stream_sync(s))) rc = b2::fail(B200FFT_ERR_CUDA, b2::rt::last_error());
+    if (s) {
+        b2::rt::stream_sync(s);
+        b2::rt::stream_destroy(s);
+    }
+    if (d) b2::rt::dfree(d);
+    return rc;
 }
 
 const char* b200fft_last_error(void) { return b2::g_last_error.c_str(); }

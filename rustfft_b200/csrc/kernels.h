@@ -767,6 +767,7 @@ struct SmoothPassKernel {
         //   MODE 2, conv 2: out[b n_outer + scatter[k]] = conj(v)                                                 (Rader)
         //   MODE 2, conv 3: k < n_outer: out[b n_outer + k] = conj(v) * chirp[k]                                  (Bluestein)
         uint32_t conv, n_outer;
+        uint32_t swap_out;  // MODE 1 as a stand-alone column pass (2-D plans): re/im swap on the store too (inverse direction)
         const uint32_t* gather;
         const uint32_t* scatter;
         const cx<T>* chirp;
@@ -892,7 +893,7 @@ struct SmoothPassKernel {
                 cx<T>* dst = p.out + (uint64_t)b * p.NN + c;
                 B2_UNROLL
                 for (int m = 0; m < R; ++m) {
-                    const cx<T> v = (MODE == 2 && SW) ? swap_ri(a[m]) : a[m];
+                    const cx<T> v = ((MODE == 2 && SW) || (MODE == 1 && p.swap_out)) ? swap_ri(a[m]) : a[m];
                     cx<T>* d = dst + (uint64_t)(base + (uint32_t)m * pp) * p.other;
                     if (MODE == 2) st_cs(d, v); else *d = v;  // pass A's output is re-read from L2 by pass B
                 }

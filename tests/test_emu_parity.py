@@ -100,6 +100,14 @@ def test_real_fft_wrappers(lib, rdtype):
     real_fft_cases.check_real_fft(rb.RealFftPlanner(rdtype, lib=lib), rdtype)
 
 
+def test_fft_2d(planner):
+    """2-D plans (tests/fft2d_cases.py): the width-point plan over the rows + one strided column pass."""
+    import fft2d_cases
+
+    pl, dtype = planner
+    fft2d_cases.check_fft2d(pl, dtype, fft2d_cases.SHAPES[:-1])
+
+
 def test_random_smooth_composites(planner):
     """Seeded random products of primes <= 31 between the one-pass limit and 600 000: every radix list / split the
     planner can produce for SmoothFourStep, against the f64 truth."""

@@ -286,6 +286,24 @@ def test_real_fft_wrappers(torch_cuda, rdtype):
     assert rel_l2(back.cpu().numpy() / n, x) <= 2 * strict_bound(n, X.dtype)
 
 
+def test_fft_2d(planner, torch_cuda):
+    """2-D plans (tests/fft2d_cases.py): host entry point against numpy fft2, device entry point equal to it bit for bit."""
+    import fft2d_cases
+
+    torch = torch_cuda
+    pl, dtype = planner
+    fft2d_cases.check_fft2d(pl, dtype)
+    h, w, batch = 270, 480, 5
+    f = pl.plan_fft_2d(h, w)
+    x = signal(batch * h * w, dtype, seed=2)
+    y = x.copy()
+    f.process(y)
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty_like(d)
+    f.process_device(d, out=out)
+    assert np.array_equal(out.cpu().numpy(), y)
+
+
 def test_host_pipeline_many_chunks(torch_cuda):
     """Host-slice path with more 64 MiB staging chunks than ring slots (4): 6.x chunks, pageable and pinned."""
     torch = torch_cuda
