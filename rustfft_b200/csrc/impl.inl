@@ -1974,12 +1974,18 @@ struct Builder {
         base.smem_bytes = (uint32_t)(((2ull * F * M + F) * sizeof(C) + 15) / 16 * 16);
         const size_t max_smem = (2ull * CONV_SMOOTH_MAX + 64) * sizeof(C) + 16;
         const uint32_t n_steps = 2 * (uint32_t)radices.size();
+        // virtual transform indices of a launch stay below 2^31 (the kernel divides them by r0 in 32 bits); whole CTAs per segment
+        const uint64_t seg = std::max<uint64_t>(F / r0, (((1ull << 31) - 1) / r0) / (F / r0) * (F / r0));
         pl.exec = [=](const ExecCtx& c) {
-            typename KT::Params q = base;
-            q.in = (const C*)c.in;
-            q.out = (C*)c.out;
-            q.n_fft = c.batch;
-            return rt::launch_loop<KT>(q, (c.batch * r0 + F - 1) / F, n_steps, q.smem_bytes, max_smem, c.stream);
+            for (uint64_t b0 = 0; b0 < c.batch; b0 += seg) {
+                const uint64_t nb = std::min(seg, c.batch - b0);
+                typename KT::Params q = base;
+                q.in = (const C*)c.in + b0 * n;
+                q.out = (C*)c.out + b0 * n;
+                q.n_fft = nb;
+                if (!rt::launch_loop<KT>(q, (nb * r0 + F - 1) / F, n_steps, q.smem_bytes, max_smem, c.stream)) return false;
+            }
+            return true;
         };
         pl.launches = [](uint64_t) { return (uint64_t)1; };
         const std::string inner = "Smooth{" + std::to_string(M) + "=" + radix_string(radices) + "}";

@@ -246,7 +246,10 @@ static bool launch_cluster(const typename KT::Params& p, uint64_t clusters, stre
         g_err = "grid too large";
         return false;
     }
-    if (cluster_max_active<KT>() <= 0) return false;
+    if (cluster_max_active<KT>() <= 0) {
+        if (g_err.empty()) g_err = "thread-block clusters of this size cannot be launched on this device";
+        return false;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * KT::C), 1, 1);
     cfg.blockDim = dim3(KT::NT, 1, 1);
